@@ -1,0 +1,134 @@
+/*
+ * asoftmax_b200.h -- C ABI of the B200-native A-softmax (SphereFace angular-margin) head.
+ *
+ * Drop-in boundary for the classifier-FC + softmax-CE slot of medivhna/TF_Face_Toolbox.
+ * The reference has no C/FFI boundary: its boundary is the Python
+ * method contract between the tower wrapper and the Network object.  Each entry point
+ * below names the reference interface it replaces:
+ *
+ *   asm_create / asm_destroy     the `classifier/fc_classifier` variable scope + graph build
+ *                                of the head        nets/sphere.py:84-90, data_parallel.py:215-224
+ *   asm_forward_backward         forward(images, labels, num_classes=..) -> logits,
+ *                                loss_function(scope, labels, **logits) -> losses,
+ *                                tf.gradients(total_loss, params)
+ *                                                   data_parallel.py:220, :223, :32-38
+ *   asm_forward                  the forward half only (loss + optional logits)
+ *                                                   nets/sphere.py:78-95, :103-118
+ *   asm_forward_partial /        one class shard's share of the same step; they replace the
+ *   asm_backward_partial         replicated-FC gradient all-reduce nccl.all_sum(grads)
+ *                                                   data_parallel.py:175-181
+ *   asm_lambda                   the lambda-annealing schedule driven by global_step
+ *                                                   train.py:157, data_parallel.py:252-253
+ *
+ * Conventions: every function returns 0 (ASM_OK) or a negative asm_status; nothing throws
+ * or aborts.  All buffers are DEVICE pointers, caller-owned and borrowed for the duration
+ * of the stream-ordered work.  Calls are asynchronous on `cuda_stream` (a cudaStream_t
+ * passed as void*); the caller synchronises.  One handle per (device, shard); a handle is
+ * not thread-safe, distinct handles are independent.  Layouts follow the reference:
+ * X [B, D] row-major fp32, W / dW [D, C_local] row-major fp32 (tf fully_connected [in,out],
+ * nets/sphere.py:86), labels [B] int32 (data.py:259) or int64.
+ */
+#ifndef ASOFTMAX_B200_H_
+#define ASOFTMAX_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct asm_head asm_head; /* opaque */
+
+typedef enum {
+  ASM_OK = 0,
+  ASM_ERR_INVALID_ARG = -1,   /* bad shape / NULL pointer / unsupported m or mode */
+  ASM_ERR_CUDA = -2,          /* a CUDA runtime / driver call failed (see asm_last_error) */
+  ASM_ERR_NO_DEVICE = -3,     /* no sm_100 device: there is NO CPU fallback */
+  ASM_ERR_LABEL_RANGE = -4,   /* a label was outside [0, C_total) (asm_check_labels) */
+  ASM_ERR_ALLOC = -5
+} asm_status;
+
+enum { ASM_MODE_FP32 = 0, ASM_MODE_BF16 = 1 };
+
+typedef struct {
+  int32_t D;             /* embedding dim (512 in every BASELINE config)            */
+  int32_t C_total;       /* num_classes (data.py:54)                                */
+  int32_t C_local;       /* classes owned by this shard                             */
+  int32_t class_offset;  /* shard owns [class_offset, class_offset + C_local)       */
+  int32_t B_max;         /* largest (global) batch this handle will see             */
+  int32_t m;             /* margin, 1..4                                            */
+  int32_t mode;          /* ASM_MODE_FP32 | ASM_MODE_BF16 (bf16 operands, fp32 acc) */
+  int32_t rank, world;   /* informational; world == 1 -> single shard               */
+  void*   nccl_comm;     /* reserved, must be NULL: collectives are issued by the
+                            host between asm_forward_partial / asm_backward_partial */
+} asm_config;
+
+/* Bytes of device workspace asm_create will allocate for cfg (0 on invalid cfg). */
+size_t asm_workspace_bytes(const asm_config* cfg);
+
+int asm_create(asm_head** out, const asm_config* cfg);
+int asm_destroy(asm_head* h);
+
+/* Last error text for this handle (or for a failed asm_create when h == NULL). */
+const char* asm_last_error(const asm_head* h);
+
+/* lambda(it) = max(lambda_min, base * (1 + gamma*it)^(-power)), it counted from 1. */
+float asm_lambda(int64_t iteration, float base, float gamma, float power, float lambda_min);
+
+/*
+ * Whole step on one shard that owns every class (world == 1).
+ *   X        [B, D] fp32                       labels [B] int32 (label_bytes 4) or int64 (8)
+ *   W        [D, C_local] fp32 master weights  lambda  host scalar (asm_lambda)
+ *   loss_out device float: mean over the batch of softmax-CE on the margin logits
+ *   logits_out_or_null  [B, C_local] fp32 margin-modified logits f, or NULL (bench path:
+ *                       the logit matrix is never written to HBM)
+ *   dX [B, D] fp32, dW [D, C_local] fp32  (gradients of loss_out)
+ */
+int asm_forward_backward(asm_head* h, const float* X, int32_t B,
+                         const void* labels, int32_t label_bytes, const float* W,
+                         float lambda, float* loss_out, float* logits_out_or_null,
+                         float* dX, float* dW, void* cuda_stream);
+
+/* Forward only: loss (+ optional logits). world == 1. */
+int asm_forward(asm_head* h, const float* X, int32_t B, const void* labels,
+                int32_t label_bytes, const float* W, float lambda, float* loss_out,
+                float* logits_out_or_null, void* cuda_stream);
+
+/*
+ * Class-sharded step, phase 1.  X / labels are the GATHERED global batch (all B rows);
+ * W is this shard's [D, C_local] slice.  Writes stats_out [3, B] fp32:
+ *   row 0: local max_j f_ij   row 1: local sum_j exp(f_ij - max)   row 2: f_{i,y_i} if this
+ *   shard owns class y_i else 0.
+ * The host all-gathers stats_out over the shards ([world, 3, B]) and calls phase 2.
+ */
+int asm_forward_partial(asm_head* h, const float* X, int32_t B, const void* labels,
+                        int32_t label_bytes, const float* W, float lambda,
+                        float* stats_out, float* logits_out_or_null, void* cuda_stream);
+
+/*
+ * Phase 2.  stats_all [n_shards, 3, B] fp32 (this shard's own stats included).  Must
+ * follow asm_forward_partial on the same handle / stream with the same X, labels, W.
+ *   loss_out   device float, global-batch mean loss (identical on every shard)
+ *   dX_partial [B, D] fp32: this shard's contribution; sum over shards (reduce-scatter)
+ *              gives dX.  The r_i * x_i term is added by the shard that owns class y_i.
+ *   dW         [D, C_local] fp32: complete for this shard -- no collective on dW.
+ */
+int asm_backward_partial(asm_head* h, const float* stats_all, int32_t n_shards,
+                         float* loss_out, float* dX_partial, float* dW, void* cuda_stream);
+
+/* Synchronises `cuda_stream` and reports whether the last step saw a label outside
+ * [0, C_total): ASM_OK or ASM_ERR_LABEL_RANGE.  (Out-of-range labels never fault the
+ * kernels: the row is treated as having no target on this shard.) */
+int asm_check_labels(asm_head* h, void* cuda_stream);
+
+/* Number of kernels the last asm_* step call launched on its stream (for bench.py). */
+int asm_last_launch_count(const asm_head* h);
+
+/* Version / build info string, e.g. "asoftmax_b200 0.1 sm_100a". */
+const char* asm_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ASOFTMAX_B200_H_ */

@@ -1,0 +1,251 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the float64 oracle.
+
+Tolerances are BASELINE.json's: exact label / argmax indexing, loss within 1e-5 relative
+(fp32 mode) / 2e-3 relative (bf16 mode), gradient cosine similarity >= 0.9999.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import asoftmax_ref as ref
+from tf_face_toolbox_b200 import ASoftmaxHead, ASoftmaxLoss, LambdaState, asoftmax_head
+from tf_face_toolbox_b200 import _lib
+from tf_face_toolbox_b200.synthetic import make_inputs
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+LOSS_TOL = {"fp32": 1e-5, "bf16": 2e-3}
+
+
+def cosine(a, b):
+    a = np.asarray(a, dtype=np.float64).ravel()
+    b = np.asarray(b, dtype=np.float64).ravel()
+    return float(a @ b / np.sqrt((a @ a) * (b @ b)))
+
+
+def run_gpu(inp, m, lam, mode, return_logits=False):
+    dev = torch.device("cuda:0")
+    loss, logits, dX, dW = asoftmax_head(inp.X.to(dev), inp.y.to(dev), inp.W.shape[1], m, lam,
+                                         weights=inp.W.to(dev), mode=mode, return_logits=return_logits,
+                                         check_labels=True)
+    torch.cuda.synchronize()
+    return (float(loss), None if logits is None else logits.cpu().numpy(), dX.cpu().numpy(), dW.cpu().numpy())
+
+
+def check_against_oracle(inp, m, lam, mode, logits=False, cos_min=0.9999):
+    r = ref.asoftmax_head(inp.X.numpy(), inp.W.numpy(), inp.y.numpy(), m, lam)
+    loss, f, dX, dW = run_gpu(inp, m, lam, mode, return_logits=logits)
+    assert np.isfinite(loss)
+    assert abs(loss - r.loss) <= LOSS_TOL[mode] * abs(r.loss), (loss, r.loss)
+    assert cosine(dX, r.dX) >= cos_min, cosine(dX, r.dX)
+    assert cosine(dW, r.dW) >= cos_min, cosine(dW, r.dW)
+    if mode == "fp32":
+        np.testing.assert_allclose(dX, r.dX, rtol=2e-3, atol=1e-6 * np.abs(r.dX).max() + 1e-12)
+        np.testing.assert_allclose(dW, r.dW, rtol=2e-3, atol=1e-5 * np.abs(r.dW).max() + 1e-12)
+    if logits:
+        tol = 1e-4 if mode == "fp32" else 0.35
+        np.testing.assert_allclose(f, r.logits, atol=tol, rtol=1e-4 if mode == "fp32" else 2e-2)
+        # exact label indexing: the margin-modified entry sits exactly at column y_i
+        rows = np.arange(f.shape[0])
+        y = inp.y.numpy()
+        S = (inp.X.double().numpy() @ (inp.W.double().numpy() / r.c))
+        moved = np.abs(S - r.logits) > 1e-9
+        assert np.array_equal(np.nonzero(moved.any(axis=1))[0], rows[moved[rows, y]])
+        # argmax equal wherever the oracle's top-2 gap exceeds the mode tolerance
+        top2 = np.sort(r.logits, axis=1)[:, -2:]
+        clear = (top2[:, 1] - top2[:, 0]) > (1e-3 if mode == "fp32" else 0.7)
+        assert np.array_equal(f.argmax(axis=1)[clear], r.logits.argmax(axis=1)[clear])
+    return loss, dX, dW, r
+
+
+# ------------------------------------------------------------------------- fp32 mode
+@pytest.mark.parametrize("B,D,C", [(37, 64, 1000), (5, 16, 7), (130, 48, 1001), (256, 128, 2049)])
+@pytest.mark.parametrize("m", [1, 2, 3, 4])
+def test_fp32_small_shapes_all_margins(B, D, C, m):
+    inp = make_inputs(B, D, C, seed=100 + m, w_std=0.05)
+    check_against_oracle(inp, m, 5.0, "fp32", logits=True)
+
+
+@pytest.mark.parametrize("lam", [0.0, 5.0, 1000 / 1.12])
+def test_fp32_lambda_values(lam):
+    inp = make_inputs(64, 128, 3000, seed=5)
+    check_against_oracle(inp, 4, lam, "fp32", logits=True)
+
+
+def test_fp32_cfg1_full_size():
+    """BASELINE config 1: head alone, m=4, D=512, C=10,572, batch 256, fp32."""
+    inp = make_inputs(256, 512, 10572)
+    check_against_oracle(inp, 4, 5.0, "fp32", logits=True)
+
+
+def test_fp32_golden_fixtures_through_c_abi():
+    z = np.load(os.path.join(GOLD, "asoftmax_small.npz"))
+    for key in [k[:-5] for k in z.files if k.endswith("_loss")]:
+        B, D, C, m = (int(v) for v in z[key + "_shape"])
+        lam = float(z[key + "_lam"])
+        inp = make_inputs(B, D, C, seed=int(z[key + "_seed"]), w_std=0.05)
+        loss, f, dX, dW = run_gpu(inp, m, lam, "fp32", return_logits=True)
+        assert abs(loss - float(z[key + "_loss"])) <= 1e-5 * abs(float(z[key + "_loss"]))
+        assert cosine(dX, z[key + "_dX"]) >= 0.99999
+        assert cosine(dW, z[key + "_dW"]) >= 0.99999
+        np.testing.assert_allclose(f, z[key + "_logits"], atol=2e-5, rtol=1e-4)
+
+
+# ------------------------------------------------------------------------- bf16 mode
+@pytest.mark.parametrize("B,D,C", [(128, 64, 256), (100, 128, 1000), (512, 512, 10572), (300, 192, 777)])
+def test_bf16_shapes(B, D, C):
+    inp = make_inputs(B, D, C, seed=21)
+    check_against_oracle(inp, 4, 5.0, "bf16", logits=True)
+
+
+@pytest.mark.parametrize("m,lam", [(1, 0.0), (2, 1.0), (3, 5.0), (4, 0.0), (4, 1000 / 1.12)])
+def test_bf16_margins_and_lambdas(m, lam):
+    inp = make_inputs(256, 512, 4000, seed=31)
+    check_against_oracle(inp, m, lam, "bf16")
+
+
+def test_bf16_matches_fp32_path_on_device():
+    inp = make_inputs(512, 512, 10572, seed=3)
+    l32, _, dX32, dW32 = run_gpu(inp, 4, 5.0, "fp32")
+    l16, _, dX16, dW16 = run_gpu(inp, 4, 5.0, "bf16")
+    assert abs(l16 - l32) <= 2e-3 * abs(l32)
+    assert cosine(dX16, dX32) >= 0.9999
+    assert cosine(dW16, dW32) >= 0.9999
+
+
+def test_bf16_cfg3_full_size_vs_oracle_and_properties():
+    """BASELINE config 3 (the metric): C=85,742, D=512, batch 512, bf16 -- against the oracle
+    and through size-independent properties (dW_j orthogonal to w_j, column-scale invariance)."""
+    inp = make_inputs(512, 512, 85742)
+    loss, dX, dW, r = check_against_oracle(inp, 4, 5.0, "bf16")
+    W = inp.W.double().numpy()
+    # normalisation Jacobian: dW_j . w_j = 0 (relative to |dW_j||w_j|)
+    num = np.abs((dW.astype(np.float64) * W).sum(axis=0))
+    den = np.sqrt((dW.astype(np.float64) ** 2).sum(axis=0) * (W ** 2).sum(axis=0)) + 1e-30
+    assert np.median(num / den) < 2e-2
+    # scale invariance: W * diag(alpha) leaves loss and dX unchanged, dW columns scale by 1/alpha
+    g = torch.Generator().manual_seed(9)
+    alpha = torch.exp2(torch.randint(-2, 3, (85742,), generator=g).float())   # powers of two: exact in bf16
+    inp2 = type(inp)(inp.X, (inp.W * alpha).contiguous(), inp.y)
+    loss2, _, dX2, dW2 = run_gpu(inp2, 4, 5.0, "bf16")
+    assert abs(loss2 - loss) <= 1e-5 * abs(loss)
+    assert cosine(dX2, dX) >= 0.999999
+    assert cosine(dW2 * alpha.numpy(), dW) >= 0.999999
+
+
+# ------------------------------------------------------------------------- interface
+def test_forward_only_and_logits_null_path():
+    inp = make_inputs(64, 128, 3000, seed=5)
+    dev = torch.device("cuda:0")
+    r = ref.asoftmax_head(inp.X.numpy(), inp.W.numpy(), inp.y.numpy(), 4, 5.0)
+    loss, logits, dX, dW = asoftmax_head(inp.X.to(dev), inp.y.to(dev), 3000, 4, 5.0, weights=inp.W.to(dev),
+                                         mode="fp32", compute_grads=False)
+    assert logits is None and dX is None and dW is None
+    assert abs(float(loss) - r.loss) <= 1e-5 * r.loss
+
+
+def test_int64_labels_and_lambda_state():
+    inp = make_inputs(64, 128, 3000, seed=5)
+    dev = torch.device("cuda:0")
+    st = LambdaState()
+    st.step()
+    assert st.value() == pytest.approx(1000 / 1.12)
+    r = ref.asoftmax_head(inp.X.numpy(), inp.W.numpy(), inp.y.numpy(), 4, st.value())
+    loss, *_ = asoftmax_head(inp.X.to(dev), inp.y.long().to(dev), 3000, 4, st, weights=inp.W.to(dev), mode="fp32")
+    assert abs(float(loss) - r.loss) <= 1e-5 * r.loss
+    assert _lib.load().asm_lambda(1, 1000.0, 0.12, 1.0, 5.0) == pytest.approx(ref.lambda_schedule(1), rel=1e-6)
+
+
+def test_label_out_of_range_is_reported_not_fatal():
+    inp = make_inputs(32, 64, 100, seed=5)
+    dev = torch.device("cuda:0")
+    y = inp.y.clone()
+    y[3] = 100
+    with pytest.raises(_lib.AsmError) as ei:
+        asoftmax_head(inp.X.to(dev), y.to(dev), 100, 4, 5.0, weights=inp.W.to(dev), mode="fp32", check_labels=True)
+    assert ei.value.code == _lib.ASM_ERR_LABEL_RANGE
+    # the device is still healthy
+    check_against_oracle(inp, 4, 5.0, "fp32")
+
+
+def test_invalid_arguments_raise():
+    inp = make_inputs(32, 64, 100, seed=5)
+    dev = torch.device("cuda:0")
+    with pytest.raises(RuntimeError):
+        asoftmax_head(inp.X, inp.y, 100, 4, 5.0, weights=inp.W, mode="fp32")          # CPU tensors
+    with pytest.raises(ValueError):
+        asoftmax_head(inp.X.to(dev), inp.y.to(dev), 101, 4, 5.0, weights=inp.W.to(dev), mode="fp32")
+    with pytest.raises(_lib.AsmError):
+        asoftmax_head(inp.X.to(dev), inp.y.to(dev), 100, 5, 5.0, weights=inp.W.to(dev), mode="fp32")  # m=5
+
+
+def test_network_shaped_wrapper_and_autograd_bridge():
+    dev = torch.device("cuda:0")
+    inp = make_inputs(64, 128, 500, seed=8)
+    head = ASoftmaxHead(128, 500, m=4, mode="fp32", device=dev, return_logits=True)
+    head.weights.copy_(inp.W.to(dev))
+    out = head.forward(inp.X.to(dev), inp.y.to(dev), num_classes=500, is_training=True)
+    losses, names, others = head.loss_function("TOWER_0", inp.y.to(dev), **out)
+    assert names == ["cross_entropy", "reg_loss"]
+    lam = ref.lambda_schedule(1)
+    assert others["lambda"] == pytest.approx(lam)
+    r = ref.asoftmax_head(inp.X.numpy(), inp.W.numpy(), inp.y.numpy(), 4, lam)
+    assert abs(float(losses[0]) - r.loss) <= 1e-5 * r.loss
+    assert float(losses[1]) == pytest.approx(0.5 * 5e-4 * float((inp.W ** 2).sum()), rel=1e-5)
+    dX, dW = head.gradients(num_gpus=1)
+    assert cosine(dX.cpu().numpy(), r.dX) >= 0.99999
+    assert cosine(dW.cpu().numpy(), r.dW + 5e-4 * inp.W.numpy()) >= 0.99999
+    assert head.forward(inp.X.to(dev), is_training=False) is not None
+    # autograd bridge
+    X = inp.X.to(dev).requires_grad_(True)
+    W = inp.W.to(dev).requires_grad_(True)
+    loss = ASoftmaxLoss.apply(X, W, inp.y.to(dev), 4, 5.0, "fp32")
+    (2.0 * loss).backward()
+    r5 = ref.asoftmax_head(inp.X.numpy(), inp.W.numpy(), inp.y.numpy(), 4, 5.0)
+    assert cosine(X.grad.cpu().numpy(), 2 * r5.dX) >= 0.99999
+    np.testing.assert_allclose(W.grad.cpu().numpy(), 2 * r5.dW, rtol=5e-3, atol=1e-5 * np.abs(r5.dW).max())
+
+
+# ------------------------------------------------------------------------- class shards
+@pytest.mark.parametrize("mode,G", [("fp32", 3), ("bf16", 2), ("bf16", 8)])
+def test_class_sharded_partials_equal_unsharded(mode, G):
+    """Run G class shards one after another on one GPU through asm_forward_partial /
+    asm_backward_partial and combine them like the collectives would."""
+    import ctypes as C
+    from tf_face_toolbox_b200.sharded import _CudaShard, shard_bounds
+    dev = torch.device("cuda:0")
+    B, D, Cn = 96, 128, 5000
+    inp = make_inputs(B, D, Cn, seed=77)
+    X, y = inp.X.to(dev), inp.y.to(dev)
+    shards = []
+    for g in range(G):
+        lo, hi = shard_bounds(Cn, G, g)
+        sh = _CudaShard(D, Cn, lo, hi, 4, mode, g, G, dev)
+        Wg = inp.W[:, lo:hi].contiguous().to(dev)
+        shards.append((sh, Wg, lo, hi))
+    stats = [sh.forward_partial(X, y, Wg, 5.0) for sh, Wg, _, _ in shards]
+    stats_all = torch.stack(stats).contiguous()
+    dX = torch.zeros(B, D, device=dev)
+    dW = torch.empty(D, Cn, device=dev)
+    losses = []
+    for sh, Wg, lo, hi in shards:
+        loss, dXp, dWg = sh.backward_partial(stats_all, X, Wg)
+        dX += dXp
+        dW[:, lo:hi] = dWg
+        losses.append(float(loss))
+    torch.cuda.synchronize()
+    r = ref.asoftmax_head(inp.X.numpy(), inp.W.numpy(), inp.y.numpy(), 4, 5.0)
+    assert max(losses) - min(losses) == 0.0
+    assert abs(losses[0] - r.loss) <= LOSS_TOL[mode] * r.loss
+    assert cosine(dX.cpu().numpy(), r.dX) >= 0.9999
+    assert cosine(dW.cpu().numpy(), r.dW) >= 0.9999
+
+
+def test_repeatable_bitwise():
+    inp = make_inputs(256, 512, 4000, seed=31)
+    a = run_gpu(inp, 4, 5.0, "bf16")
+    b = run_gpu(inp, 4, 5.0, "bf16")
+    assert a[0] == b[0]
+    assert np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3])

@@ -1,0 +1,351 @@
+// C ABI of libasoftmax_b200 (see include/asoftmax_b200.h): handle, workspace carving and
+// the stream-ordered launch sequence of one A-softmax head step.  No CPU fallback: without
+// an sm_100 device asm_create fails with ASM_ERR_NO_DEVICE.
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <new>
+
+#include "../../include/asoftmax_b200.h"
+#include "asm_kernels.cuh"
+
+using namespace asmh;
+
+struct asm_head {
+  asm_config cfg;
+  int device = 0;
+  int num_sms = 148;
+  int Cp = 0;
+  int NT = 0;
+  char* ws = nullptr;            // single device allocation
+  size_t ws_bytes = 0;
+  Step st{};                     // pointers into ws + per-step state
+  size_t dx_part_capacity = 0;   // floats
+  UmmaMaps maps{};
+  int maps_B = -1;
+  UmmaTuning tune{8192, 1024, 2048};
+  bool fwd_valid = false;
+  int launches = 0;
+  char err[512];
+};
+
+namespace {
+thread_local char g_create_err[512] = "";
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct Layout {
+  size_t ylocal, flags, n, inv_n, inv_c, tgt_s, tgt_f, part, stats_local, lse, gtarget, rcoef,
+      q_part, coef, G, dx_part, Xb, Wb, total;
+  int Cp, NT, MT;
+  size_t dx_capacity;
+};
+
+bool valid_cfg(const asm_config* c) {
+  if (!c) return false;
+  if (c->D <= 0 || c->D % 16 != 0) return false;
+  if (c->C_total <= 0 || c->C_local <= 0 || c->class_offset < 0) return false;
+  if ((long long)c->class_offset + c->C_local > c->C_total) return false;
+  if (c->B_max <= 0 || c->m < 1 || c->m > 4) return false;
+  if (c->mode != ASM_MODE_FP32 && c->mode != ASM_MODE_BF16) return false;
+  if (c->mode == ASM_MODE_BF16 && c->D % 64 != 0) return false;
+  if (c->world < 1 || c->rank < 0 || c->rank >= c->world) return false;
+  if (c->nccl_comm != nullptr) return false;
+  return true;
+}
+
+Layout make_layout(const asm_config& c, int num_sms) {
+  Layout L{};
+  const size_t B = c.B_max, D = c.D;
+  L.Cp = (int)align_up(c.C_local, 256);
+  L.NT = (L.Cp + 127) / 128;
+  L.MT = (int)((B + kRowTileHost - 1) / kRowTileHost);
+  // dX split-K partial capacity: the larger of both paths at B_max, but never less than
+  // what a single 128-row tile would use (KS grows when B shrinks).
+  const int ks_simt = simt_dx_splits(c.B_max, c.D, L.Cp);
+  const int ks_umma = umma_dx_splits(c.B_max, c.D, L.Cp, num_sms);
+  const int ks_one = c.mode == ASM_MODE_BF16 ? umma_dx_splits(128, c.D, L.Cp, num_sms)
+                                             : simt_dx_splits(128, c.D, L.Cp);
+  const size_t cap_full = (size_t)(c.mode == ASM_MODE_BF16 ? ks_umma : ks_simt) * B * D;
+  const size_t cap_one = (size_t)ks_one * (B < 128 ? B : 128) * D;
+  L.dx_capacity = cap_full > cap_one ? cap_full : cap_one;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+  L.ylocal = take(B * 4);
+  L.flags = take(256);
+  L.n = take(B * 4);
+  L.inv_n = take(B * 4);
+  L.inv_c = take((size_t)L.Cp * 4);
+  L.tgt_s = take(B * 4);
+  L.tgt_f = take(B * 4);
+  L.part = take(B * (size_t)L.NT * 8);
+  L.stats_local = take(3 * B * 4);
+  L.lse = take(B * 4);
+  L.gtarget = take(B * 4);
+  L.rcoef = take(B * 4);
+  L.q_part = take((size_t)L.MT * L.Cp * 4);
+  L.coef = take((size_t)L.Cp * 4);
+  L.G = take(B * (size_t)L.Cp * (c.mode == ASM_MODE_BF16 ? 2 : 4));
+  L.dx_part = take(L.dx_capacity * 4);
+  if (c.mode == ASM_MODE_BF16) {
+    L.Xb = take(B * D * 2);
+    L.Wb = take(D * (size_t)L.Cp * 2);
+  }
+  L.total = off;
+  return L;
+}
+
+int fail(asm_head* h, int code, const char* fmt, const char* detail) {
+  char* dst = h ? h->err : g_create_err;
+  snprintf(dst, 512, fmt, detail ? detail : "");
+  return code;
+}
+
+#define CU_TRY(h, expr)                                                         \
+  do {                                                                          \
+    cudaError_t e__ = (expr);                                                   \
+    if (e__ != cudaSuccess) return fail(h, ASM_ERR_CUDA, #expr ": %s", cudaGetErrorString(e__)); \
+  } while (0)
+
+int check_launch(asm_head* h, const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    snprintf(h->err, 512, "%s: %s", what, cudaGetErrorString(e));
+    return ASM_ERR_CUDA;
+  }
+  return ASM_OK;
+}
+
+// forward half up to stats_local; shared by every entry point
+int run_forward(asm_head* h, const float* X, int B, const void* labels, int label_bytes,
+                const float* W, float lambda, float* logits, cudaStream_t stream) {
+  if (!h) return ASM_ERR_INVALID_ARG;
+  if (!X || !labels || !W) return fail(h, ASM_ERR_INVALID_ARG, "null input pointer%s", "");
+  if (B <= 0 || B > h->cfg.B_max) return fail(h, ASM_ERR_INVALID_ARG, "B out of range%s", "");
+  if (label_bytes != 4 && label_bytes != 8)
+    return fail(h, ASM_ERR_INVALID_ARG, "label_bytes must be 4 or 8%s", "");
+  if (!(lambda >= 0.f)) return fail(h, ASM_ERR_INVALID_ARG, "lambda must be >= 0%s", "");
+  Step& s = h->st;
+  s.B = B;
+  s.lambda = lambda;
+  s.invB = 1.0f / (float)B;
+  s.X = X;
+  s.W = W;
+  s.logits = logits;
+  s.MT = (B + kRowTileHost - 1) / kRowTileHost;
+  h->launches = 0;
+  h->fwd_valid = false;
+  CU_TRY(h, cudaMemsetAsync(s.flags, 0, 4, stream));
+  if (h->cfg.mode == ASM_MODE_BF16) {
+    s.NT = umma_forward_tiles(s.Cp);
+    s.KS = umma_dx_splits(B, s.D, s.Cp, h->num_sms);
+    if (h->maps_B != B) {
+      if (!umma_build_maps(&h->maps, s))
+        return fail(h, ASM_ERR_CUDA, "cuTensorMapEncodeTiled failed%s", "");
+      h->maps_B = B;
+    }
+  } else {
+    s.NT = simt_forward_tiles(s.C);
+    s.KS = simt_dx_splits(B, s.D, s.Cp);
+  }
+  while (s.KS > 1 && (size_t)s.KS * B * s.D > h->dx_part_capacity) --s.KS;
+  launch_prep(s, labels, label_bytes, stream);
+  h->launches += 1;
+  if (h->cfg.mode == ASM_MODE_BF16) launch_umma_forward(s, h->maps, h->tune, h->num_sms, stream);
+  else launch_simt_forward(s, stream);
+  h->launches += 1;
+  launch_combine_local(s, stream);
+  h->launches += 1;
+  int rc = check_launch(h, "forward launch");
+  if (rc == ASM_OK) h->fwd_valid = true;
+  return rc;
+}
+
+int run_backward(asm_head* h, const float* stats_all, int n_shards, float* loss_out,
+                 float* dX, float* dW, bool grads, cudaStream_t stream) {
+  Step& s = h->st;
+  s.loss = loss_out;
+  s.dX = dX;
+  s.dW = dW;
+  launch_combine_global(s, stats_all, n_shards, stream);
+  h->launches += 1;
+  if (grads) {
+    if (h->cfg.mode == ASM_MODE_BF16) {
+      launch_umma_backward(s, h->maps, h->tune, h->num_sms, stream);
+      h->launches += 4;
+    } else {
+      launch_simt_backward(s, stream);
+      h->launches += 3;
+    }
+    launch_dx_finish(s, stream);
+    h->launches += 1;
+  }
+  return check_launch(h, "backward launch");
+}
+}  // namespace
+
+extern "C" {
+
+const char* asm_version(void) { return "asoftmax_b200 0.1 sm_100a"; }
+
+float asm_lambda(int64_t iteration, float base, float gamma, float power, float lambda_min) {
+  const double v = (double)base * pow(1.0 + (double)gamma * (double)iteration, -(double)power);
+  return (float)(v > (double)lambda_min ? v : (double)lambda_min);
+}
+
+size_t asm_workspace_bytes(const asm_config* cfg) {
+  if (!valid_cfg(cfg)) return 0;
+  return make_layout(*cfg, 148).total;
+}
+
+int asm_create(asm_head** out, const asm_config* cfg) {
+  if (!out) return fail(nullptr, ASM_ERR_INVALID_ARG, "out is NULL%s", "");
+  *out = nullptr;
+  if (!valid_cfg(cfg)) return fail(nullptr, ASM_ERR_INVALID_ARG, "invalid asm_config%s", "");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(nullptr, ASM_ERR_NO_DEVICE, "no CUDA device (this library has no CPU fallback)%s", "");
+  }
+  int dev = 0, major = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess)
+    return fail(nullptr, ASM_ERR_CUDA, "cudaGetDevice failed%s", "");
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (major != 10)
+    return fail(nullptr, ASM_ERR_NO_DEVICE, "device is not sm_100 (Blackwell B200) %s", "");
+  asm_head* h = new (std::nothrow) asm_head();
+  if (!h) return fail(nullptr, ASM_ERR_ALLOC, "host allocation failed%s", "");
+  h->cfg = *cfg;
+  h->device = dev;
+  h->num_sms = sms > 0 ? sms : 148;
+  h->err[0] = 0;
+  const char* e;
+  if ((e = getenv("ASM_UMMA_MN_LBO"))) h->tune.mn_lbo = (uint32_t)atoi(e);
+  if ((e = getenv("ASM_UMMA_MN_SBO"))) h->tune.mn_sbo = (uint32_t)atoi(e);
+  if ((e = getenv("ASM_UMMA_MN_KSTEP"))) h->tune.mn_kstep = (uint32_t)atoi(e);
+  const Layout L = make_layout(*cfg, h->num_sms);
+  cudaError_t ce = cudaMalloc(&h->ws, L.total);
+  if (ce != cudaSuccess) {
+    fail(nullptr, ASM_ERR_ALLOC, "cudaMalloc(workspace): %s", cudaGetErrorString(ce));
+    delete h;
+    return ASM_ERR_ALLOC;
+  }
+  h->ws_bytes = L.total;
+  cudaMemset(h->ws, 0, L.total);
+  if (cfg->mode == ASM_MODE_BF16) {
+    ce = umma_configure();
+    if (ce != cudaSuccess) {
+      fail(nullptr, ASM_ERR_CUDA, "cudaFuncSetAttribute(smem): %s", cudaGetErrorString(ce));
+      cudaFree(h->ws);
+      delete h;
+      return ASM_ERR_CUDA;
+    }
+  }
+  Step& s = h->st;
+  s.D = cfg->D;
+  s.C = cfg->C_local;
+  s.Cp = L.Cp;
+  s.C_total = cfg->C_total;
+  s.class_offset = cfg->class_offset;
+  s.m = cfg->m;
+  s.mode = cfg->mode;
+  char* w = h->ws;
+  s.ylocal = (int*)(w + L.ylocal);
+  s.flags = (int*)(w + L.flags);
+  s.n = (float*)(w + L.n);
+  s.inv_n = (float*)(w + L.inv_n);
+  s.inv_c = (float*)(w + L.inv_c);
+  s.tgt_s = (float*)(w + L.tgt_s);
+  s.tgt_f = (float*)(w + L.tgt_f);
+  s.part = (float2*)(w + L.part);
+  s.stats_local = (float*)(w + L.stats_local);
+  s.lse = (float*)(w + L.lse);
+  s.gtarget = (float*)(w + L.gtarget);
+  s.rcoef = (float*)(w + L.rcoef);
+  s.q_part = (float*)(w + L.q_part);
+  s.coef = (float*)(w + L.coef);
+  s.G = (void*)(w + L.G);
+  s.dx_part = (float*)(w + L.dx_part);
+  h->dx_part_capacity = L.dx_capacity;
+  if (cfg->mode == ASM_MODE_BF16) {
+    s.Xb = (__nv_bfloat16*)(w + L.Xb);
+    s.Wb = (__nv_bfloat16*)(w + L.Wb);
+  }
+  h->Cp = L.Cp;
+  *out = h;
+  return ASM_OK;
+}
+
+int asm_destroy(asm_head* h) {
+  if (!h) return ASM_ERR_INVALID_ARG;
+  if (h->ws) cudaFree(h->ws);
+  delete h;
+  return ASM_OK;
+}
+
+const char* asm_last_error(const asm_head* h) { return h ? h->err : g_create_err; }
+
+int asm_last_launch_count(const asm_head* h) { return h ? h->launches : 0; }
+
+int asm_forward_partial(asm_head* h, const float* X, int32_t B, const void* labels,
+                        int32_t label_bytes, const float* W, float lambda, float* stats_out,
+                        float* logits_out_or_null, void* cuda_stream) {
+  cudaStream_t stream = (cudaStream_t)cuda_stream;
+  int rc = run_forward(h, X, B, labels, label_bytes, W, lambda, logits_out_or_null, stream);
+  if (rc != ASM_OK) return rc;
+  if (!stats_out) return fail(h, ASM_ERR_INVALID_ARG, "stats_out is NULL%s", "");
+  CU_TRY(h, cudaMemcpyAsync(stats_out, h->st.stats_local, (size_t)3 * B * sizeof(float),
+                            cudaMemcpyDeviceToDevice, stream));
+  return ASM_OK;
+}
+
+int asm_backward_partial(asm_head* h, const float* stats_all, int32_t n_shards, float* loss_out,
+                         float* dX_partial, float* dW, void* cuda_stream) {
+  if (!h) return ASM_ERR_INVALID_ARG;
+  if (!h->fwd_valid)
+    return fail(h, ASM_ERR_INVALID_ARG, "asm_backward_partial without asm_forward_partial%s", "");
+  if (!stats_all || n_shards < 1 || !dX_partial || !dW)
+    return fail(h, ASM_ERR_INVALID_ARG, "null pointer / bad n_shards%s", "");
+  return run_backward(h, stats_all, n_shards, loss_out, dX_partial, dW, true,
+                      (cudaStream_t)cuda_stream);
+}
+
+int asm_forward_backward(asm_head* h, const float* X, int32_t B, const void* labels,
+                         int32_t label_bytes, const float* W, float lambda, float* loss_out,
+                         float* logits_out_or_null, float* dX, float* dW, void* cuda_stream) {
+  cudaStream_t stream = (cudaStream_t)cuda_stream;
+  if (h && h->cfg.C_local != h->cfg.C_total)
+    return fail(h, ASM_ERR_INVALID_ARG,
+                "asm_forward_backward needs a shard that owns every class; use the partial calls%s", "");
+  int rc = run_forward(h, X, B, labels, label_bytes, W, lambda, logits_out_or_null, stream);
+  if (rc != ASM_OK) return rc;
+  if (!loss_out || !dX || !dW) return fail(h, ASM_ERR_INVALID_ARG, "null output pointer%s", "");
+  return run_backward(h, h->st.stats_local, 1, loss_out, dX, dW, true, stream);
+}
+
+int asm_forward(asm_head* h, const float* X, int32_t B, const void* labels, int32_t label_bytes,
+                const float* W, float lambda, float* loss_out, float* logits_out_or_null,
+                void* cuda_stream) {
+  cudaStream_t stream = (cudaStream_t)cuda_stream;
+  if (h && h->cfg.C_local != h->cfg.C_total)
+    return fail(h, ASM_ERR_INVALID_ARG, "asm_forward needs a shard that owns every class%s", "");
+  int rc = run_forward(h, X, B, labels, label_bytes, W, lambda, logits_out_or_null, stream);
+  if (rc != ASM_OK) return rc;
+  if (!loss_out) return fail(h, ASM_ERR_INVALID_ARG, "loss_out is NULL%s", "");
+  return run_backward(h, h->st.stats_local, 1, loss_out, nullptr, nullptr, false, stream);
+}
+
+int asm_check_labels(asm_head* h, void* cuda_stream) {
+  if (!h) return ASM_ERR_INVALID_ARG;
+  int flags = 0;
+  CU_TRY(h, cudaMemcpyAsync(&flags, h->st.flags, 4, cudaMemcpyDeviceToHost,
+                            (cudaStream_t)cuda_stream));
+  CU_TRY(h, cudaStreamSynchronize((cudaStream_t)cuda_stream));
+  if (flags & 1) return fail(h, ASM_ERR_LABEL_RANGE, "label outside [0, C_total)%s", "");
+  return ASM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,87 @@
+// Kernel launchers shared between translation units of libasoftmax_b200.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace asmh {
+
+// Everything one step needs; filled by the host API (asm_api.cu), passed by value.
+constexpr int kRowTileHost = 128;   // == asmh::kRowTile (asm_common.cuh)
+
+struct Step {
+  // problem
+  int B, D, C, Cp, C_total, class_offset, m, mode;
+  float lambda, invB;
+  // caller buffers (device)
+  const float* X;            // [B, D]
+  const float* W;            // [D, C]
+  float* logits;             // [B, C] or null
+  float* dX;                 // [B, D]
+  float* dW;                 // [D, C]
+  float* loss;               // scalar
+  // workspace (device)
+  int* ylocal;               // [B]   y - class_offset if owned else -1
+  int* flags;                // [1]   bit0: label out of range
+  float* n;                  // [B]
+  float* inv_n;              // [B]
+  float* inv_c;              // [Cp]  1/||w_j|| (0 on pad columns)
+  float* tgt_s;              // [B]   s_{i,y} (owner shard only)
+  float* tgt_f;              // [B]   f_{i,y}
+  float2* part;              // [B, NT] per-column-tile (max, sumexp)
+  int NT;                    // number of column tiles of the forward kernel
+  float* stats_local;        // [3, B]
+  float* lse;                // [B]   M_i + log Z_i (global)
+  float* gtarget;            // [B]   G'_{i,y_i}
+  float* rcoef;              // [B]   r_i  (0 if not owned)
+  float* q_part;             // [MT, Cp] column sums  sum_i G'_ij s_ij per 128-row tile
+  int MT;
+  float* coef;               // [Cp]  q_j / c_j^2  (dW normalisation-Jacobian correction)
+  void* G;                   // [B, Cp]  G'' = G' * inv_c   (fp32 or bf16 by mode)
+  float* dx_part;            // [KS, B, D] split-K partials of dX
+  int KS;
+  __nv_bfloat16* Xb;         // [B, D]    bf16 mode
+  __nv_bfloat16* Wb;         // [D, Cp]   bf16 mode
+};
+
+// prep: column norms of W (+ bf16 copy), row norms of X (+ bf16 copy), label localisation
+void launch_prep(const Step& s, const void* labels, int label_bytes, cudaStream_t st);
+// combine per-tile (max,sumexp) partials into stats_local [3,B]
+void launch_combine_local(const Step& s, cudaStream_t st);
+// combine [n_shards,3,B] stats into lse / loss / target coefficients
+void launch_combine_global(const Step& s, const float* stats_all, int n_shards, cudaStream_t st);
+// dX = sum_z dx_part[z] + r_i x_i
+void launch_dx_finish(const Step& s, cudaStream_t st);
+
+// fp32 (CUDA-core) contractions with fused epilogues
+void launch_simt_forward(const Step& s, cudaStream_t st);
+void launch_simt_backward(const Step& s, cudaStream_t st);   // G'' + q_part, dW, dx_part
+int simt_forward_tiles(int C);                               // NT for the fp32 path
+int simt_dx_splits(int B, int D, int Cp);
+
+// q_part -> coef[j] = (sum_t q_part[t][j]) * inv_c[j]^2
+void launch_dw_coef(const Step& s, cudaStream_t st);
+
+// bf16 (tcgen05 / TMEM / TMA) contractions with fused epilogues
+struct UmmaMaps {            // TMA descriptors over the bf16 workspace operands
+  CUtensorMap xb_k, xb_mn, wb_mn, wb_k, g_k, g_mn;
+};
+struct UmmaTuning {          // MN-major shared-memory descriptor parameters (bytes)
+  uint32_t mn_lbo, mn_sbo, mn_kstep;
+};
+struct UmmaArgs {
+  int mt, nt, ks, kb_total, kb_per;
+  uint64_t desc_hi_k, desc_hi_mn;
+  uint32_t kstep_mn;
+};
+cudaError_t umma_configure();
+bool umma_build_maps(UmmaMaps* m, const Step& s);
+int umma_forward_tiles(int Cp);
+int umma_dx_splits(int B, int D, int Cp, int num_sms);
+void launch_umma_forward(const Step& s, const UmmaMaps& m, const UmmaTuning& tu, int num_sms,
+                         cudaStream_t st);
+void launch_umma_backward(const Step& s, const UmmaMaps& m, const UmmaTuning& tu, int num_sms,
+                          cudaStream_t st);
+
+}  // namespace asmh

@@ -1,0 +1,228 @@
+// HBM-bound kernels of the A-softmax head: norms (+ bf16 operand copies), stats combine,
+// dX finish.  See DESIGN.md "Kernels" for the per-kernel roofline and algorithmic bytes.
+#include "asm_common.cuh"
+#include "asm_kernels.cuh"
+
+namespace asmh {
+
+// ---------------------------------------------------------------------------------------
+// prep: one launch, two roles.
+//   blocks [0, nwb): W role. Block (32 x 8) owns 64 columns; thread (tx, ty) owns the column
+//     pair 2*(blk*32+tx) and the rows ty, ty+8, ...  Loads are coalesced along C (a warp
+//     reads 256 contiguous bytes per row), the bf16 copy is written with the same mapping
+//     (128 B per warp per row) into the padded pitch Cp, and the 8 row groups are reduced
+//     through shared memory into inv_c[j] = 1/||w_j||.  W is read exactly once.
+//   blocks [nwb, ...): X role. One warp per embedding row: n_i, 1/n_i, bf16 copy, and the
+//     label -> local-class-index translation with the range check.
+// ---------------------------------------------------------------------------------------
+template <bool VEC2, bool BF16>
+__global__ void __launch_bounds__(256) prep_kernel(Step s, const void* labels, int label_bytes,
+                                                   int nwb) {
+  __shared__ float red[8][64];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  if ((int)blockIdx.x < nwb) {
+    const int j0 = (blockIdx.x * 32 + tx) * 2;
+    float a0 = 0.f, a1 = 0.f;
+    if (j0 < s.Cp) {
+      const bool v0 = j0 < s.C, v1 = j0 + 1 < s.C;
+      const float* w = s.W + j0;
+      __nv_bfloat16* wb = BF16 ? s.Wb + j0 : nullptr;
+#pragma unroll 8
+      for (int d = ty; d < s.D; d += 8) {
+        float x0 = 0.f, x1 = 0.f;
+        if (VEC2) {
+          if (v1) {
+            const float2 v = __ldg(reinterpret_cast<const float2*>(w + (size_t)d * s.C));
+            x0 = v.x; x1 = v.y;
+          } else if (v0) {
+            x0 = __ldg(w + (size_t)d * s.C);
+          }
+        } else {
+          if (v0) x0 = __ldg(w + (size_t)d * s.C);
+          if (v1) x1 = __ldg(w + (size_t)d * s.C + 1);
+        }
+        a0 = fmaf(x0, x0, a0);
+        a1 = fmaf(x1, x1, a1);
+        if (BF16)
+          *reinterpret_cast<__nv_bfloat162*>(wb + (size_t)d * s.Cp) = __floats2bfloat162_rn(x0, x1);
+      }
+    }
+    red[ty][tx * 2] = a0;
+    red[ty][tx * 2 + 1] = a1;
+    __syncthreads();
+    const int t = ty * 32 + tx;
+    if (t < 64) {
+      float acc = 0.f;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) acc += red[r][t];
+      const int j = blockIdx.x * 64 + t;
+      if (j < s.Cp) s.inv_c[j] = (j < s.C && acc > 0.f) ? rsqrtf(acc) : 0.f;
+    }
+  } else {
+    const int row = (blockIdx.x - nwb) * 8 + ty;
+    if (row >= s.B) return;
+    const float* x = s.X + (size_t)row * s.D;
+    float acc = 0.f;
+    for (int d = tx; d < s.D; d += 32) {
+      const float v = __ldg(x + d);
+      acc = fmaf(v, v, acc);
+      if (BF16) s.Xb[(size_t)row * s.D + d] = __float2bfloat16_rn(v);
+    }
+    acc = warp_sum(acc);
+    if (tx == 0) {
+      const float nn = sqrtf(acc);
+      s.n[row] = nn;
+      s.inv_n[row] = nn > 0.f ? 1.0f / nn : 0.f;
+      long long y = label_bytes == 8 ? reinterpret_cast<const long long*>(labels)[row]
+                                     : (long long)reinterpret_cast<const int*>(labels)[row];
+      if (y < 0 || y >= s.C_total) atomicOr(s.flags, 1);
+      const long long yl = y - s.class_offset;
+      s.ylocal[row] = (yl >= 0 && yl < s.C) ? (int)yl : -1;
+      s.tgt_s[row] = 0.f;
+      s.tgt_f[row] = 0.f;
+    }
+  }
+}
+
+void launch_prep(const Step& s, const void* labels, int label_bytes, cudaStream_t st) {
+  const int nwb = (s.Cp + 63) / 64;
+  const int nxb = (s.B + 7) / 8;
+  const bool vec2 = (s.C % 2 == 0) && ((reinterpret_cast<uintptr_t>(s.W) & 7) == 0);
+  dim3 blk(32, 8);
+  dim3 grd(nwb + nxb);
+  if (s.mode == 1) {
+    if (vec2) prep_kernel<true, true><<<grd, blk, 0, st>>>(s, labels, label_bytes, nwb);
+    else prep_kernel<false, true><<<grd, blk, 0, st>>>(s, labels, label_bytes, nwb);
+  } else {
+    if (vec2) prep_kernel<true, false><<<grd, blk, 0, st>>>(s, labels, label_bytes, nwb);
+    else prep_kernel<false, false><<<grd, blk, 0, st>>>(s, labels, label_bytes, nwb);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// combine_local: one warp per row reduces the per-column-tile (max, sumexp) partials.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) combine_local_kernel(Step s) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= s.B) return;
+  float m = -INFINITY, z = 0.f;
+  const float2* p = s.part + (size_t)row * s.NT;
+  for (int t = lane; t < s.NT; t += 32) {
+    const float2 v = p[t];
+    ms_combine(m, z, v.x, v.y);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float m2 = __shfl_xor_sync(0xffffffffu, m, o);
+    const float z2 = __shfl_xor_sync(0xffffffffu, z, o);
+    ms_combine(m, z, m2, z2);
+  }
+  if (lane == 0) {
+    s.stats_local[row] = m;
+    s.stats_local[s.B + row] = z;
+    s.stats_local[2 * s.B + row] = s.ylocal[row] >= 0 ? s.tgt_f[row] : 0.f;
+  }
+}
+
+void launch_combine_local(const Step& s, cudaStream_t st) {
+  combine_local_kernel<<<(s.B + 7) / 8, 256, 0, st>>>(s);
+}
+
+// ---------------------------------------------------------------------------------------
+// combine_global: one block.  Per row: M = max_g m_g, Z = sum_g z_g e^{m_g - M},
+// lse = M + log Z, loss_i = lse - f_y; then the target-column gradient coefficients
+//   g_y = (e^{f_y - lse} - 1)/B,  G'_y = g_y (lambda + psi')/(1 + lambda),
+//   r   = g_y (psi - t psi') / ((1 + lambda) n)            
+// and the deterministic tree-reduced mean loss.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) combine_global_kernel(Step s, const float* stats_all,
+                                                              int n_shards) {
+  __shared__ float red[1024];
+  float acc = 0.f;
+  for (int row = threadIdx.x; row < s.B; row += 1024) {
+    float M = -INFINITY;
+    for (int g = 0; g < n_shards; ++g) M = fmaxf(M, stats_all[(size_t)g * 3 * s.B + row]);
+    float Z = 0.f, fy = 0.f;
+    for (int g = 0; g < n_shards; ++g) {
+      const float* sg = stats_all + (size_t)g * 3 * s.B;
+      const float mg = sg[row];
+      if (mg > -INFINITY) Z += sg[s.B + row] * expf(mg - M);
+      fy += sg[2 * s.B + row];
+    }
+    const float lse = M + logf(Z);
+    s.lse[row] = lse;
+    acc += lse - fy;
+    float gt = 0.f, r = 0.f;
+    if (s.ylocal[row] >= 0) {
+      const float sy = s.tgt_s[row], n = s.n[row], inv_n = s.inv_n[row];
+      float psi, dpsi;
+      const float t = fminf(1.f, fmaxf(-1.f, sy * inv_n));
+      psi_eval(t, s.m, psi, dpsi);
+      const float gy = (expf(s.tgt_f[row] - lse) - 1.0f) * s.invB;
+      const float il = 1.0f / (1.0f + s.lambda);
+      gt = gy * (s.lambda + dpsi) * il;
+      r = gy * (psi - t * dpsi) * il * inv_n;
+      (void)n;
+    }
+    s.gtarget[row] = gt;
+    s.rcoef[row] = r;
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 512; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && s.loss) *s.loss = red[0] * s.invB;
+}
+
+void launch_combine_global(const Step& s, const float* stats_all, int n_shards, cudaStream_t st) {
+  combine_global_kernel<<<1, 1024, 0, st>>>(s, stats_all, n_shards);
+}
+
+// ---------------------------------------------------------------------------------------
+// dw_coef: coef[j] = (sum over row tiles of q_part[t][j]) / c_j^2
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dw_coef_kernel(Step s) {
+  const int j = blockIdx.x * 256 + threadIdx.x;
+  if (j >= s.Cp) return;
+  float q = 0.f;
+  for (int t = 0; t < s.MT; ++t) q += s.q_part[(size_t)t * s.Cp + j];
+  const float ic = s.inv_c[j];
+  s.coef[j] = q * ic * ic;
+}
+
+void launch_dw_coef(const Step& s, cudaStream_t st) {
+  dw_coef_kernel<<<(s.Cp + 255) / 256, 256, 0, st>>>(s);
+}
+
+// ---------------------------------------------------------------------------------------
+// dx_finish: dX = sum_z dx_part[z] + r_i * x_i   (float4 along D; D % 4 == 0)
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dx_finish_kernel(Step s) {
+  const size_t total4 = (size_t)s.B * s.D / 4;
+  const size_t stride4 = total4;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total4;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const int row = (int)((i * 4) / s.D);
+    const float r = s.rcoef[row];
+    const float4 x = __ldg(reinterpret_cast<const float4*>(s.X) + i);
+    float4 a = make_float4(r * x.x, r * x.y, r * x.z, r * x.w);
+    const float4* p = reinterpret_cast<const float4*>(s.dx_part) + i;
+    for (int z = 0; z < s.KS; ++z) {
+      const float4 v = p[(size_t)z * stride4];
+      a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    }
+    reinterpret_cast<float4*>(s.dX)[i] = a;
+  }
+}
+
+void launch_dx_finish(const Step& s, cudaStream_t st) {
+  const size_t total4 = (size_t)s.B * s.D / 4;
+  int blocks = (int)((total4 + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  dx_finish_kernel<<<blocks, 256, 0, st>>>(s);
+}
+
+}  // namespace asmh

@@ -1,0 +1,277 @@
+"""Python host side of the A-softmax head: the call surface the reference's towers use.
+
+Reference contract mirrored here (file:line in /root/reference):
+  * data_parallel.py:220   logits = model.forward(images, labels, num_classes=..., is_training=True)
+  * data_parallel.py:223   losses, losses_name, others = model.loss_function(scope, labels, **logits)
+  * data_parallel.py:32-38 tf.gradients(total_loss, params) scaled by mult_lr * 1/num_gpus
+  * nets/sphere.py:84-90   classifier/fc_classifier weights [D, C], N(0, 0.001) init, no bias, L2 reg
+  * nets/sphere.py:103-118 losses = [cross_entropy, reg_loss]
+  * train.py:157 + data_parallel.py:252-253  global_step, the lambda-annealing clock
+
+`asoftmax_head(...)` is the functional entry point named by BASELINE.json's north_star:
+(embeddings, labels, num_classes, m, lambda state) -> (loss, logits | None, dX, dW).
+`ASoftmaxHead` wraps it in the forward / loss_function / param_list shape of
+nets/net_base.py:80-101, and `ASoftmaxLoss` exposes it to torch autograd so a torch
+backbone can be trained through it.  Everything executes in libasoftmax_b200.so
+(hand-written sm_100a CUDA) through ctypes; torch only owns the device buffers and the
+stream.  There is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from collections import OrderedDict
+from dataclasses import dataclass
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import _lib
+
+
+# --------------------------------------------------------------------------------------
+# lambda annealing state (host scalar; kernels are stateless)
+# --------------------------------------------------------------------------------------
+@dataclass
+class LambdaState:
+    """SphereFace schedule lambda(it) = max(lambda_min, base * (1 + gamma*it)^(-power)).
+
+    `iteration` plays the role of global_step (train.py:157): `step()` is the analogue of
+    `global_step.assign_add(1)` (data_parallel.py:252-253) and the first training step uses
+    it = 1.  `explicit` overrides the schedule with a fixed lambda.
+    """
+    iteration: int = 0
+    base: float = 1000.0
+    gamma: float = 0.12
+    power: float = 1.0
+    lambda_min: float = 5.0
+    explicit: Optional[float] = None
+
+    def value(self) -> float:
+        if self.explicit is not None:
+            return float(self.explicit)
+        return max(self.lambda_min, self.base * (1.0 + self.gamma * self.iteration) ** (-self.power))
+
+    def step(self) -> float:
+        self.iteration += 1
+        return self.value()
+
+
+def _as_lambda(lambda_state) -> float:
+    if lambda_state is None:
+        return 0.0
+    if isinstance(lambda_state, LambdaState):
+        return lambda_state.value()
+    return float(lambda_state)
+
+
+# --------------------------------------------------------------------------------------
+# handle cache: one asm_head per (device, shard geometry, B_max, m, mode)
+# --------------------------------------------------------------------------------------
+class _Handle:
+    def __init__(self, device: torch.device, D: int, C_total: int, C_local: int, class_offset: int,
+                 B_max: int, m: int, mode: str, rank: int = 0, world: int = 1):
+        self.lib = _lib.load()
+        if device.type != "cuda":
+            raise RuntimeError("the A-softmax head runs on a CUDA (B200) device only; no CPU fallback")
+        self.device = device
+        self.cfg = _lib.AsmConfig(D, C_total, C_local, class_offset, B_max, m, _lib.MODES[mode],
+                                  rank, world, None)
+        self.ptr = C.c_void_p()
+        with torch.cuda.device(device):
+            rc = self.lib.asm_create(C.byref(self.ptr), C.byref(self.cfg))
+        if rc != _lib.ASM_OK:
+            raise _lib.AsmError(rc, (self.lib.asm_last_error(None) or b"").decode())
+
+    def close(self):
+        if self.ptr:
+            self.lib.asm_destroy(self.ptr)
+            self.ptr = C.c_void_p()
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_HANDLES: Dict[tuple, _Handle] = {}
+
+
+def _round_batch(B: int) -> int:
+    return max(128, (B + 127) // 128 * 128)
+
+
+def get_handle(device, D, C_total, C_local, class_offset, B, m, mode, rank=0, world=1) -> _Handle:
+    device = torch.device(device)
+    if device.index is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    key = (device.index, D, C_total, C_local, class_offset, _round_batch(B), m, mode, rank, world)
+    h = _HANDLES.get(key)
+    if h is None:
+        h = _Handle(device, D, C_total, C_local, class_offset, _round_batch(B), m, mode, rank, world)
+        _HANDLES[key] = h
+    return h
+
+
+def release_handles() -> None:
+    for h in _HANDLES.values():
+        h.close()
+    _HANDLES.clear()
+
+
+def _check_inputs(embeddings, labels, weights, num_classes):
+    if not (embeddings.is_cuda and labels.is_cuda and weights.is_cuda):
+        raise RuntimeError("embeddings, labels and weights must be CUDA tensors (no CPU fallback)")
+    if embeddings.dtype != torch.float32 or weights.dtype != torch.float32:
+        raise TypeError("embeddings and weights must be float32 (bf16 rounding happens inside the library)")
+    if labels.dtype not in (torch.int32, torch.int64):
+        raise TypeError("labels must be int32 (reference dtype, data.py:259) or int64")
+    if embeddings.dim() != 2 or weights.dim() != 2 or labels.dim() != 1:
+        raise ValueError("expected embeddings [B,D], weights [D,C], labels [B]")
+    if embeddings.shape[1] != weights.shape[0] or labels.shape[0] != embeddings.shape[0]:
+        raise ValueError("shape mismatch between embeddings / weights / labels")
+    if num_classes is not None and weights.shape[1] != num_classes:
+        raise ValueError(f"weights has {weights.shape[1]} classes, num_classes={num_classes}")
+
+
+def asoftmax_head(embeddings: torch.Tensor, labels: torch.Tensor, num_classes: int, m: int = 4,
+                  lambda_state=None, *, weights: torch.Tensor, mode: str = "bf16",
+                  return_logits: bool = False, compute_grads: bool = True,
+                  check_labels: bool = False
+                  ) -> Tuple[torch.Tensor, Optional[torch.Tensor], Optional[torch.Tensor], Optional[torch.Tensor]]:
+    """A-softmax head forward + backward on one GPU that owns every class.
+
+    embeddings [B, D] fp32, labels [B] int32/int64, weights [D, num_classes] fp32 (the
+    `classifier/fc_classifier/weights` variable, nets/sphere.py:86), margin m in 1..4,
+    lambda_state a LambdaState or a float.  Returns (loss, logits | None, dX, dW): loss is the
+    batch-mean softmax cross-entropy over the margin logits (nets/sphere.py:109), logits are
+    the margin-modified f (only when return_logits: the benchmark path never writes the
+    [B, C] matrix to HBM), dX / dW are d(loss)/d(embeddings, weights).
+    Asynchronous on the current CUDA stream.
+    """
+    _check_inputs(embeddings, labels, weights, num_classes)
+    X = embeddings.contiguous()
+    W = weights.contiguous()
+    y = labels.contiguous()
+    B, D = X.shape
+    Cn = W.shape[1]
+    h = get_handle(X.device, D, Cn, Cn, 0, B, m, mode)
+    lam = _as_lambda(lambda_state)
+    loss = torch.empty(1, device=X.device, dtype=torch.float32)
+    logits = torch.empty(B, Cn, device=X.device, dtype=torch.float32) if return_logits else None
+    stream = C.c_void_p(torch.cuda.current_stream(X.device).cuda_stream)
+    with torch.cuda.device(X.device):
+        if compute_grads:
+            dX = torch.empty_like(X)
+            dW = torch.empty_like(W)
+            rc = h.lib.asm_forward_backward(
+                h.ptr, X.data_ptr(), B, y.data_ptr(), y.element_size(), W.data_ptr(), lam,
+                loss.data_ptr(), logits.data_ptr() if logits is not None else None,
+                dX.data_ptr(), dW.data_ptr(), stream)
+        else:
+            dX = dW = None
+            rc = h.lib.asm_forward(
+                h.ptr, X.data_ptr(), B, y.data_ptr(), y.element_size(), W.data_ptr(), lam,
+                loss.data_ptr(), logits.data_ptr() if logits is not None else None, stream)
+        _lib.check(rc, h.ptr)
+        if check_labels:
+            _lib.check(h.lib.asm_check_labels(h.ptr, stream), h.ptr)
+    return loss[0], logits, dX, dW
+
+
+def last_launch_count(device, D, C_total, B, m, mode) -> int:
+    h = get_handle(device, D, C_total, C_total, 0, B, m, mode)
+    return int(h.lib.asm_last_launch_count(h.ptr))
+
+
+# --------------------------------------------------------------------------------------
+# torch autograd bridge: lets a torch backbone train through the fused head
+# --------------------------------------------------------------------------------------
+class ASoftmaxLoss(torch.autograd.Function):
+    """loss = ASoftmaxLoss.apply(embeddings, weights, labels, m, lam, mode).  The fused call
+    already produced dX and dW, so backward only scales them by the incoming gradient."""
+
+    @staticmethod
+    def forward(ctx, embeddings, weights, labels, m, lam, mode):
+        loss, _, dX, dW = asoftmax_head(embeddings, labels, weights.shape[1], m, lam,
+                                        weights=weights, mode=mode)
+        ctx.save_for_backward(dX, dW)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        dX, dW = ctx.saved_tensors
+        return grad_out * dX, grad_out * dW, None, None, None, None
+
+
+# --------------------------------------------------------------------------------------
+# Network-shaped wrapper: forward / loss_function / param_list of nets/net_base.py:80-101
+# --------------------------------------------------------------------------------------
+class ASoftmaxHead:
+    """The `classifier` scope of a margin network, as DataParallel_margin drives it.
+
+        logits = head.forward(features, labels, num_classes=C, is_training=True)   # data_parallel.py:220
+        losses, names, others = head.loss_function(scope, labels, **logits)        # data_parallel.py:223
+        dX, dW = head.gradients()                                                   # data_parallel.py:32-38
+
+    `features` are the backbone's embeddings (the reference passes images to the full
+    network; the head is the part after `features = self.backbone(images)`, nets/sphere.py:82).
+    """
+    name = "classifier"
+
+    def __init__(self, num_features: int, num_classes: int, m: int = 4, weight_decay: float = 5e-4,
+                 mode: str = "bf16", device="cuda", lambda_state: Optional[LambdaState] = None,
+                 return_logits: bool = False, seed: Optional[int] = None):
+        gen = None
+        if seed is not None:
+            gen = torch.Generator(device="cpu").manual_seed(seed)
+        # weights_initializer=tf.random_normal_initializer(stddev=0.001)  (nets/sphere.py:87)
+        w = torch.randn(num_features, num_classes, generator=gen, dtype=torch.float32) * 0.001
+        self.weights = w.to(device)                  # classifier/fc_classifier/weights [D, C]
+        self.num_classes = num_classes
+        self.m = m
+        self.weight_decay = weight_decay
+        self.mode = mode
+        self.lambda_state = lambda_state if lambda_state is not None else LambdaState()
+        self.return_logits = return_logits
+        self._last = None
+
+    # nets/net_base.py:84-86, margin form data_parallel.py:220
+    def forward(self, features, labels=None, num_classes=None, is_training=True):
+        if not is_training:
+            return features                           # nets/sphere.py:96-101: bare features
+        assert num_classes is not None, "num_classes must be given when is_training=True"
+        assert labels is not None, "a margin head needs labels in forward (data_parallel.py:220)"
+        lam = self.lambda_state.step()                # global_step += 1, first step uses it = 1
+        loss, logits, dX, dW = asoftmax_head(features, labels, num_classes, self.m, lam,
+                                             weights=self.weights, mode=self.mode,
+                                             return_logits=self.return_logits)
+        self._last = dict(loss=loss, dX=dX, dW=dW, lam=lam)
+        out = {"logits": logits, "features": features}
+        return out
+
+    # nets/net_base.py:88-90; nets/sphere.py:103-118
+    def loss_function(self, scope, labels, **logits):
+        assert self._last is not None, "forward(...) must run first"
+        losses = [self._last["loss"]]
+        losses_name = ["cross_entropy"]
+        # _regularize (nets/net_base.py:103-107): contrib l2_regularizer = wd * sum(w^2)/2
+        reg = 0.5 * self.weight_decay * (self.weights * self.weights).sum()
+        losses.append(reg)
+        losses_name.append("reg_loss")
+        others = OrderedDict()
+        others["lambda"] = self._last["lam"]
+        return losses, losses_name, others
+
+    def gradients(self, num_gpus: int = 1, mult_lr: float = 1.0):
+        """(dX, dW) of the cross-entropy term, scaled like _grad_var (data_parallel.py:37).
+        The L2 term's gradient wd * W is added to dW as tf.gradients(total_loss) would."""
+        s = mult_lr / num_gpus
+        dW = self._last["dW"] + self.weight_decay * self.weights
+        return self._last["dX"] * s, dW * s
+
+    def param_list(self, is_training=True, trainable=True, scope=None):
+        return [[self.weights]] if is_training else []
+
+    def mult_lr_list(self, scope=None):
+        return [1.0]

@@ -1,0 +1,138 @@
+"""Class-sharded A-softmax head: one process per GPU, W partitioned by class.
+
+Replaces the reference's replicated classifier + per-variable gradient all-reduce
+(`nccl.all_sum(grads)`, data_parallel.py:175-181: a full [D, C] fp32 message per tower per
+step) with a class partition in which dW never leaves its shard.  Per step:
+
+  1. all-gather the embeddings X [B/G, D] -> [B, D] and the labels      (torch.distributed)
+  2. asm_forward_partial on the local shard -> per-row (max, sumexp, target logit | 0)
+  3. ONE all-gather of the [3, B] statistics                             (torch.distributed)
+  4. asm_backward_partial: global logsumexp / loss, G'', dW_local, dX partial
+  5. reduce-scatter dX partial [B, D] -> the owner's [B/G, D]            (torch.distributed)
+
+Semantics equal the reference's towers: per-tower mean over B/G, grads x 1/G, all_sum
+== gradient of the global-batch mean (data_parallel.py:37,179,248).  The collectives run
+through torch.distributed (NCCL over NVLink on the GPU box; gloo in the CPU tests, where
+the per-shard compute is injected by the test).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from .head import LambdaState, _as_lambda, get_handle
+
+
+def shard_bounds(num_classes: int, world: int, rank: int) -> Tuple[int, int]:
+    """Rank g owns classes [g*ceil(C/G), min(C, (g+1)*ceil(C/G)))."""
+    per = -(-num_classes // world)
+    return min(num_classes, rank * per), min(num_classes, (rank + 1) * per)
+
+
+class _CudaShard:
+    """Per-shard compute through the C ABI (asm_forward_partial / asm_backward_partial)."""
+
+    def __init__(self, D, C_total, lo, hi, m, mode, rank, world, device):
+        self.args = (D, C_total, hi - lo, lo, m, mode, rank, world)
+        self.device = torch.device(device)
+
+    def _handle(self, B):
+        D, C_total, C_local, lo, m, mode, rank, world = self.args
+        return get_handle(self.device, D, C_total, C_local, lo, B, m, mode, rank, world)
+
+    def forward_partial(self, X, y, W, lam):
+        B = X.shape[0]
+        h = self._handle(B)
+        stats = torch.empty(3, B, device=X.device, dtype=torch.float32)
+        stream = C.c_void_p(torch.cuda.current_stream(X.device).cuda_stream)
+        with torch.cuda.device(X.device):
+            _lib.check(h.lib.asm_forward_partial(h.ptr, X.data_ptr(), B, y.data_ptr(), y.element_size(),
+                                                 W.data_ptr(), lam, stats.data_ptr(), None, stream), h.ptr)
+        self._keep = (X, y, W)          # borrowed until backward_partial has been enqueued
+        return stats
+
+    def backward_partial(self, stats_all, X, W):
+        B = X.shape[0]
+        h = self._handle(B)
+        loss = torch.empty(1, device=X.device, dtype=torch.float32)
+        dXp = torch.empty_like(X)
+        dW = torch.empty_like(W)
+        stream = C.c_void_p(torch.cuda.current_stream(X.device).cuda_stream)
+        with torch.cuda.device(X.device):
+            _lib.check(h.lib.asm_backward_partial(h.ptr, stats_all.data_ptr(), stats_all.shape[0],
+                                                  loss.data_ptr(), dXp.data_ptr(), dW.data_ptr(), stream), h.ptr)
+        return loss[0], dXp, dW
+
+
+class ShardedASoftmaxHead:
+    """Class-parallel head over a torch.distributed process group (one rank per GPU)."""
+
+    def __init__(self, num_features: int, num_classes: int, m: int = 4, mode: str = "bf16",
+                 device="cuda", group=None, lambda_state: Optional[LambdaState] = None,
+                 weights_full: Optional[torch.Tensor] = None, seed: int = 0, shard_compute=None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.D, self.C, self.m, self.mode = num_features, num_classes, m, mode
+        self.lo, self.hi = shard_bounds(num_classes, self.world, self.rank)
+        if self.hi <= self.lo:
+            raise ValueError("more ranks than classes: empty shard")
+        self.device = torch.device(device)
+        if weights_full is not None:
+            w = weights_full[:, self.lo:self.hi].to(torch.float32)
+        else:   # N(0, 0.001) like nets/sphere.py:87, generated shard-locally but rank-independent
+            g = torch.Generator().manual_seed(seed)
+            w = (torch.randn(num_features, num_classes, generator=g) * 0.001)[:, self.lo:self.hi]
+        self.weights = w.contiguous().to(self.device)            # [D, C_local]
+        self.lambda_state = lambda_state if lambda_state is not None else LambdaState()
+        self.compute = shard_compute if shard_compute is not None else _CudaShard(
+            num_features, num_classes, self.lo, self.hi, m, mode, self.rank, self.world, self.device)
+
+    # ---- collectives (torch.distributed plumbing) ------------------------------------
+    def _all_gather(self, t: torch.Tensor) -> torch.Tensor:
+        if self.world == 1:
+            return t
+        out = torch.empty((self.world,) + tuple(t.shape), device=t.device, dtype=t.dtype)
+        dist.all_gather_into_tensor(out, t.contiguous(), group=self.group)
+        return out
+
+    def _reduce_scatter_rows(self, full: torch.Tensor, rows_local: int) -> torch.Tensor:
+        if self.world == 1:
+            return full
+        out = torch.empty(rows_local, full.shape[1], device=full.device, dtype=full.dtype)
+        if dist.get_backend(self.group) == "gloo":      # gloo has no reduce_scatter
+            dist.all_reduce(full, group=self.group)
+            out.copy_(full[self.rank * rows_local:(self.rank + 1) * rows_local])
+        else:
+            dist.reduce_scatter_tensor(out, full, group=self.group)
+        return out
+
+    # ---- one training step of the head -------------------------------------------------
+    def step(self, embeddings_local: torch.Tensor, labels_local: torch.Tensor, lambda_state=None):
+        """embeddings_local [B/G, D], labels_local [B/G] (this rank's data-parallel slice,
+        data_parallel.py:206-207).  Returns (loss, dX_local [B/G, D], dW_local [D, C_local]);
+        loss is the global-batch mean and identical on every rank."""
+        lam = _as_lambda(lambda_state) if lambda_state is not None else self.lambda_state.step()
+        b = embeddings_local.shape[0]
+        X = self._all_gather(embeddings_local).reshape(-1, self.D)
+        y = self._all_gather(labels_local).reshape(-1)
+        stats = self.compute.forward_partial(X, y, self.weights, lam)             # [3, B]
+        stats_all = self._all_gather(stats).reshape(self.world, 3, X.shape[0])    # [G, 3, B]
+        loss, dX_partial, dW = self.compute.backward_partial(stats_all, X, self.weights)
+        dX_local = self._reduce_scatter_rows(dX_partial, b)
+        return loss, dX_local, dW
+
+    def gather_weights(self) -> torch.Tensor:
+        """All shards -> one [D, C] fp32 tensor (`classifier/fc_classifier/weights`, the
+        layout saver.py:36-40 writes), for checkpoint compatibility."""
+        if self.world == 1:
+            return self.weights.clone()
+        per = -(-self.C // self.world)
+        pad = torch.zeros(self.D, per, device=self.weights.device, dtype=torch.float32)
+        pad[:, : self.hi - self.lo] = self.weights
+        allw = self._all_gather(pad)                                     # [G, D, per]
+        return allw.permute(1, 0, 2).reshape(self.D, -1)[:, : self.C].contiguous()
