@@ -1,0 +1,374 @@
+#!/usr/bin/env python
+"""Benchmark of the A-softmax head hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload cfg3|cfg1|cfg2_head|cfg4|cfg5_head] [--mode bf16|fp32]
+
+One "step" = one forward+backward pass of the head over one batch of synthetic input
+(everything behind asm_forward_backward: norms, contractions, epilogues; excluding the
+optimizer).  At N=1 the workload is BASELINE config 3 (C=85,742, D=512, batch 512, bf16), the
+configuration the metric is quoted on.  For N>1 (launched by torchrun, one rank per GPU) the
+same global batch is class-sharded over the ranks (strong scaling): all-gather X, one
+statistics all-gather, reduce-scatter dX -- no collective on dW.
+
+Prints ONE JSON line on rank 0 (see the keys in main()).  `--impl reference` times the CPU
+stand-in for the reference's TensorFlow path (oracle/tf_graph_port.py; the TF code itself
+cannot run) on the host cores for the same metric and config.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "A-softmax head fwd+bwd samples/sec at C=85,742 D=512, 1/2/4/8 B200"
+UNIT = "samples/s"
+M_MARGIN = 4
+LAMBDA = 5.0      # lambda_min of the SphereFace schedule (timing uses lambda=5)
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=float(d["hbm_gbs"]), tf_burst=float(d["bf16_tflops"]),
+                    tf_sustained=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback")
+
+
+# ----------------------------------------------------------------------------------------
+# clocks: sample nvidia-smi while the GPU is under the benchmark load
+# ----------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,utilization.gpu,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0: float, t1: float):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons, allsm = [], None, set(), []
+        for ts, line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                clk, mx = float(f[1]), float(f[2])
+            except ValueError:
+                continue
+            smax = mx
+            allsm.append(clk)
+            if t0 - 0.05 <= ts <= t1 + 0.15:
+                sm.append(clk)
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        use = sm if sm else allsm
+        return {"sm_mhz": statistics.median(use) if use else None, "sm_max_mhz": smax,
+                "reasons": sorted(reasons), "samples": len(use)}
+
+
+# ----------------------------------------------------------------------------------------
+# CPU stand-in for the reference (oracle/tf_graph_port.py): used ONLY as a timed baseline
+# ----------------------------------------------------------------------------------------
+def time_cpu_port(cfg, steps: int, warmup: int, budget_s: float):
+    import torch
+    from oracle import tf_graph_port as port
+    from tf_face_toolbox_b200.synthetic import make_inputs
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    inp = make_inputs(cfg["B"], cfg["D"], cfg["C"])
+    Bs = cfg["B"]
+    t = time.perf_counter()
+    port.step(inp.X, inp.W, inp.y, M_MARGIN, LAMBDA)
+    est = time.perf_counter() - t
+    # bound the run: shrink the per-step sample (rows of the batch) if K steps would not fit
+    while Bs > 64 and est * (Bs / cfg["B"]) * (steps + warmup) > budget_s:
+        Bs //= 2
+    X, y = inp.X[:Bs].contiguous(), inp.y[:Bs].contiguous()
+    for _ in range(warmup):
+        port.step(X, inp.W, y, M_MARGIN, LAMBDA)
+    times = []
+    for _ in range(steps):
+        t = time.perf_counter()
+        port.step(X, inp.W, y, M_MARGIN, LAMBDA)
+        times.append(time.perf_counter() - t)
+    total = sum(times)
+    sample = (f"full workload: {steps} steps of B={Bs} rows x C={cfg['C']} classes x D={cfg['D']}, fp32, torch-CPU"
+              if Bs == cfg["B"] else
+              f"{steps} steps over the first {Bs} of {cfg['B']} batch rows x all C={cfg['C']} classes, fp32, torch-CPU")
+    return dict(value=Bs * steps / total, ms_per_step=1e3 * total / steps, cores=cores, sample=sample, B_sample=Bs)
+
+
+def run_reference(args, cfg):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = time_cpu_port(cfg, args.steps, args.warmup, budget_s=150.0)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": workload_config(args, cfg, 1),
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "reference TensorFlow path cannot run (no TF, py2 code, missing module); timed the op-by-op torch-CPU port",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, cfg, world):
+    return {"workload": f"{args.workload}: A-softmax head fwd+bwd, C={cfg['C']} D={cfg['D']} batch={cfg['B']} "
+                        f"m={M_MARGIN} lambda={LAMBDA} {args.mode}",
+            "global_batch": cfg["B"], "num_classes": cfg["C"], "embedding_dim": cfg["D"],
+            "parallelism": f"class-sharded x{world}" if world > 1 else "single shard",
+            "l2": "inputs larger than L2 (W fp32 %.1f MB + bf16 operand copies; no explicit flush)" % (cfg["C"] * cfg["D"] * 4 / 1e6)
+                  if cfg["C"] * cfg["D"] * 4 > 126e6 else "L2 flushed between timed iterations (256 MB write)"}
+
+
+# ----------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------
+def run_ours(args, cfg):
+    import torch
+    import torch.distributed as dist
+    from tf_face_toolbox_b200 import ShardedASoftmaxHead, asoftmax_head
+    from tf_face_toolbox_b200.head import get_handle
+    from tf_face_toolbox_b200.synthetic import make_inputs
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the A-softmax head has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, D, Cn, mode = cfg["B"], cfg["D"], cfg["C"], args.mode
+    K, Wm = args.steps, args.warmup
+    peaks = load_peaks()
+    inp = make_inputs(B, D, Cn)
+    flush = None
+    need_flush = Cn * D * 4 <= 126e6
+    if need_flush:
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+
+    if world == 1:
+        Xd, yd, Wd = inp.X.to(dev), inp.y.to(dev), inp.W.to(dev)
+
+        def step():
+            return asoftmax_head(Xd, yd, Cn, M_MARGIN, LAMBDA, weights=Wd, mode=mode)
+        b_local = B
+    else:
+        if B % world:
+            raise SystemExit("global batch must divide by the number of ranks")
+        b_local = B // world
+        head = ShardedASoftmaxHead(D, Cn, m=M_MARGIN, mode=mode, device=dev, weights_full=inp.W)
+        Xd = inp.X[rank * b_local:(rank + 1) * b_local].contiguous().to(dev)
+        yd = inp.y[rank * b_local:(rank + 1) * b_local].contiguous().to(dev)
+
+        def step():
+            return head.step(Xd, yd, LAMBDA)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n):
+        """n calls of fn between CUDA events on the current stream; returns ms (max over ranks)."""
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            if flush is not None:
+                flush.zero_()
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    flush_ms = 0.0
+    if flush is not None:       # cost of the L2 flush itself, subtracted from flushed loops
+        for _ in range(3):
+            flush.zero_()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(20):
+            flush.zero_()
+        e1.record()
+        torch.cuda.synchronize()
+        flush_ms = e0.elapsed_time(e1) / 20
+
+    # ---- (1) device-resident timing: the headline `value`
+    for _ in range(max(Wm, 3)):
+        step()
+    t_load0 = time.time()
+    ms_total = timed(step, K)
+    ms_step = ms_total / K - flush_ms
+    value = B / (ms_step * 1e-3)
+
+    # ---- (2) per-kernel durations (CUDA events on the launching stream, inside the library)
+    kernels = {}
+    launches_per_step = 0
+    if world == 1:
+        h = get_handle(dev, D, Cn, Cn, 0, B, M_MARGIN, mode)
+        launches_per_step = int(h.lib.asm_last_launch_count(h.ptr))
+        h.lib.asm_set_profiling(h.ptr, 1)
+        ms_buf = (C.c_float * 16)()
+        names = C.create_string_buffer(16 * 32)
+        for _ in range(K):
+            if flush is not None:
+                flush.zero_()
+            step()
+            n = h.lib.asm_get_profile(h.ptr, 16, ms_buf, names)
+            for i in range(max(n, 0)):
+                nm = names.raw[i * 32:(i + 1) * 32].split(b"\0")[0].decode()
+                kernels.setdefault(nm, []).append(ms_buf[i])
+        h.lib.asm_set_profiling(h.ptr, 0)
+    else:
+        sh = head.compute._handle(B)
+        launches_per_step = int(sh.lib.asm_last_launch_count(sh.ptr))
+    kavg = {k: sum(v) / len(v) for k, v in kernels.items()}
+
+    # ---- (3) end to end through the public Python API with HOST buffers
+    Xh = (inp.X if world == 1 else inp.X[rank * b_local:(rank + 1) * b_local]).contiguous().pin_memory()
+    yh = (inp.y if world == 1 else inp.y[rank * b_local:(rank + 1) * b_local]).contiguous().pin_memory()
+    loss_h = torch.empty(1, dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        Xd.copy_(Xh, non_blocking=True)
+        yd.copy_(yh, non_blocking=True)
+        out = step()
+        loss_h.copy_(out[0].reshape(1), non_blocking=False)      # D2H read of the result (syncs)
+        return out
+    for _ in range(3):
+        e2e_step()
+    ms_e2e = timed(e2e_step, K) / K - flush_ms
+    t_load1 = time.time()
+    e2e_value = B / (ms_e2e * 1e-3)
+
+    # keep the GPU under the same load long enough for nvidia-smi to sample clocks
+    if rank == 0 and (t_load1 - t_load0) < 1.0:
+        t_end = time.time() + 1.2
+        while time.time() < t_end:
+            for _ in range(20):
+                step()
+            torch.cuda.synchronize()
+        t_load1 = time.time()
+    clocks = sampler.stop(t_load0, t_load1) if rank == 0 else None
+    if world > 1:
+        dist.barrier()
+
+    if rank == 0:
+        C_local = Cn if world == 1 else -(-Cn // world)
+        gemm_flops = 2.0 * B * D * C_local
+        roof_kernels = []
+        for nm, ms in kavg.items():
+            if nm in ("fwd_logits_stats", "bwd_recompute_g", "dw_gemm", "dx_gemm"):
+                ach = gemm_flops / (ms * 1e-3) / 1e12
+                roof_kernels.append({"kernel": nm, "ms": ms, "bound": "tensor", "achieved": ach, "unit": "TFLOP/s",
+                                     "frac": ach / peaks["tf_burst"]})
+            elif nm == "prep_norms":
+                Cp = (Cn + 255) // 256 * 256
+                by = 4.0 * D * Cn + (2.0 * D * Cp if mode == "bf16" else 0) + 4.0 * B * D
+                ach = by / (ms * 1e-3) / 1e9
+                roof_kernels.append({"kernel": nm, "ms": ms, "bound": "hbm", "achieved": ach, "unit": "GB/s",
+                                     "frac": ach / peaks["hbm"]})
+            else:
+                roof_kernels.append({"kernel": nm, "ms": ms})
+        dom = max((k for k in roof_kernels if "bound" in k), key=lambda k: k["ms"], default=None)
+        roofline = None
+        if dom is not None:
+            roofline = {"kernel": dom["kernel"], "bound": dom["bound"], "achieved": dom["achieved"],
+                        "peak": peaks["tf_burst"] if dom["bound"] == "tensor" else peaks["hbm"],
+                        "unit": dom["unit"], "frac": dom["frac"], "traffic": None,
+                        "peak_source": peaks["src"] + (" burst bf16" if dom["bound"] == "tensor" else " copy"),
+                        "ms": dom["ms"]}
+        step_flops = 6.0 * B * D * Cn
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(Wm, 3),
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": mode, "data": "synthetic", "config": workload_config(args, cfg, world),
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": int(b_local * D * 4 + b_local * 4), "d2h_bytes_per_step": 4},
+            "gpu_launches": launches_per_step * K,
+            "roofline": roofline,
+            "step_tensor_frac": step_flops / (ms_step * 1e-3) / 1e12 / peaks["tf_burst"],
+            "step_algorithmic_tflops": step_flops / (ms_step * 1e-3) / 1e12,
+            "kernels": roof_kernels,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            r = time_cpu_port(cfg, 8, 1, budget_s=25.0)
+            line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+                                    "sample": r["sample"]}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    from tf_face_toolbox_b200.synthetic import CONFIGS
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg3", choices=sorted(CONFIGS))
+    ap.add_argument("--mode", default=None, choices=["bf16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    cfg = dict(CONFIGS[args.workload])
+    if args.mode is None:
+        args.mode = cfg["mode"]
+    if args.impl == "reference":
+        run_reference(args, cfg)
+    else:
+        run_ours(args, cfg)
+
+
+if __name__ == "__main__":
+    main()

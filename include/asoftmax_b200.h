@@ -125,6 +125,13 @@ int asm_check_labels(asm_head* h, void* cuda_stream);
 /* Number of kernels the last asm_* step call launched on its stream (for bench.py). */
 int asm_last_launch_count(const asm_head* h);
 
+/* Per-kernel device timing for bench.py's roofline: when enabled every kernel of a step is
+ * bracketed by CUDA events on the step's stream.  asm_get_profile synchronises on the last
+ * event and writes up to max_n durations (ms) and 32-byte NUL-terminated kernel names;
+ * returns the number written (>= 0) or a negative asm_status. */
+int asm_set_profiling(asm_head* h, int enable);
+int asm_get_profile(asm_head* h, int32_t max_n, float* ms_out, char* names_out);
+
 /* Version / build info string, e.g. "asoftmax_b200 0.1 sm_100a". */
 const char* asm_version(void);
 

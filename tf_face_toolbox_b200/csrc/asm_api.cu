@@ -28,6 +28,12 @@ struct asm_head {
   UmmaTuning tune{8192, 1024, 2048};
   bool fwd_valid = false;
   int launches = 0;
+  // optional per-kernel timing (asm_set_profiling): event i is recorded before kernel i
+  bool profiling = false;
+  static constexpr int kMaxMarks = 16;
+  cudaEvent_t ev[kMaxMarks + 1] = {};
+  const char* mark_name[kMaxMarks] = {};
+  int n_marks = 0;
   char err[512];
 };
 
@@ -109,6 +115,19 @@ int fail(asm_head* h, int code, const char* fmt, const char* detail) {
     if (e__ != cudaSuccess) return fail(h, ASM_ERR_CUDA, #expr ": %s", cudaGetErrorString(e__)); \
   } while (0)
 
+// Counts a kernel launch and, when profiling, records the event that precedes it.
+void mark(asm_head* h, const char* name, cudaStream_t stream) {
+  h->launches += 1;
+  if (h->profiling && h->n_marks < asm_head::kMaxMarks) {
+    cudaEventRecord(h->ev[h->n_marks], stream);
+    h->mark_name[h->n_marks] = name;
+    h->n_marks += 1;
+  }
+}
+void mark_end(asm_head* h, cudaStream_t stream) {
+  if (h->profiling) cudaEventRecord(h->ev[h->n_marks], stream);
+}
+
 int check_launch(asm_head* h, const char* what) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
@@ -136,6 +155,7 @@ int run_forward(asm_head* h, const float* X, int B, const void* labels, int labe
   s.logits = logits;
   s.MT = (B + kRowTileHost - 1) / kRowTileHost;
   h->launches = 0;
+  h->n_marks = 0;
   h->fwd_valid = false;
   CU_TRY(h, cudaMemsetAsync(s.flags, 0, 4, stream));
   if (h->cfg.mode == ASM_MODE_BF16) {
@@ -151,13 +171,14 @@ int run_forward(asm_head* h, const float* X, int B, const void* labels, int labe
     s.KS = simt_dx_splits(B, s.D, s.Cp);
   }
   while (s.KS > 1 && (size_t)s.KS * B * s.D > h->dx_part_capacity) --s.KS;
+  mark(h, "prep_norms", stream);
   launch_prep(s, labels, label_bytes, stream);
-  h->launches += 1;
+  mark(h, "fwd_logits_stats", stream);
   if (h->cfg.mode == ASM_MODE_BF16) launch_umma_forward(s, h->maps, h->tune, h->num_sms, stream);
   else launch_simt_forward(s, stream);
-  h->launches += 1;
+  mark(h, "combine_local", stream);
   launch_combine_local(s, stream);
-  h->launches += 1;
+  mark_end(h, stream);
   int rc = check_launch(h, "forward launch");
   if (rc == ASM_OK) h->fwd_valid = true;
   return rc;
@@ -169,19 +190,25 @@ int run_backward(asm_head* h, const float* stats_all, int n_shards, float* loss_
   s.loss = loss_out;
   s.dX = dX;
   s.dW = dW;
+  const bool tc = h->cfg.mode == ASM_MODE_BF16;
+  mark(h, "combine_global", stream);
   launch_combine_global(s, stats_all, n_shards, stream);
-  h->launches += 1;
   if (grads) {
-    if (h->cfg.mode == ASM_MODE_BF16) {
-      launch_umma_backward(s, h->maps, h->tune, h->num_sms, stream);
-      h->launches += 4;
-    } else {
-      launch_simt_backward(s, stream);
-      h->launches += 3;
-    }
+    mark(h, "bwd_recompute_g", stream);
+    if (tc) launch_umma_bwdg(s, h->maps, h->tune, h->num_sms, stream);
+    else launch_simt_bwdg(s, stream);
+    mark(h, "dw_coef", stream);
+    launch_dw_coef(s, stream);
+    mark(h, "dw_gemm", stream);
+    if (tc) launch_umma_dw(s, h->maps, h->tune, h->num_sms, stream);
+    else launch_simt_dw(s, stream);
+    mark(h, "dx_gemm", stream);
+    if (tc) launch_umma_dx(s, h->maps, h->tune, h->num_sms, stream);
+    else launch_simt_dx(s, stream);
+    mark(h, "dx_finish", stream);
     launch_dx_finish(s, stream);
-    h->launches += 1;
   }
+  mark_end(h, stream);
   return check_launch(h, "backward launch");
 }
 }  // namespace
@@ -282,6 +309,8 @@ int asm_create(asm_head** out, const asm_config* cfg) {
 int asm_destroy(asm_head* h) {
   if (!h) return ASM_ERR_INVALID_ARG;
   if (h->ws) cudaFree(h->ws);
+  if (h->ev[0])
+    for (int i = 0; i <= asm_head::kMaxMarks; ++i) cudaEventDestroy(h->ev[i]);
   delete h;
   return ASM_OK;
 }
@@ -336,6 +365,34 @@ int asm_forward(asm_head* h, const float* X, int32_t B, const void* labels, int3
   if (rc != ASM_OK) return rc;
   if (!loss_out) return fail(h, ASM_ERR_INVALID_ARG, "loss_out is NULL%s", "");
   return run_backward(h, h->st.stats_local, 1, loss_out, nullptr, nullptr, false, stream);
+}
+
+int asm_set_profiling(asm_head* h, int enable) {
+  if (!h) return ASM_ERR_INVALID_ARG;
+  if (enable && !h->ev[0]) {
+    for (int i = 0; i <= asm_head::kMaxMarks; ++i) CU_TRY(h, cudaEventCreate(&h->ev[i]));
+  }
+  h->profiling = enable != 0;
+  h->n_marks = 0;
+  return ASM_OK;
+}
+
+int asm_get_profile(asm_head* h, int32_t max_n, float* ms_out, char* names_out) {
+  if (!h || !ms_out || !names_out || max_n < 0) return ASM_ERR_INVALID_ARG;
+  if (!h->profiling || h->n_marks == 0) return 0;
+  CU_TRY(h, cudaEventSynchronize(h->ev[h->n_marks]));
+  const int n = h->n_marks < max_n ? h->n_marks : max_n;
+  // marks of the forward half end at the event recorded by mark_end of run_forward; when a
+  // backward half followed, its first event was recorded right after, so consecutive
+  // differences are per-kernel durations either way.
+  for (int i = 0; i < n; ++i) {
+    float ms = 0.f;
+    CU_TRY(h, cudaEventElapsedTime(&ms, h->ev[i], h->ev[i + 1]));
+    ms_out[i] = ms;
+    strncpy(names_out + (size_t)i * 32, h->mark_name[i], 31);
+    names_out[(size_t)i * 32 + 31] = 0;
+  }
+  return n;
 }
 
 int asm_check_labels(asm_head* h, void* cuda_stream) {

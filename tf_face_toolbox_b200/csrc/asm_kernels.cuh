@@ -56,7 +56,9 @@ void launch_dx_finish(const Step& s, cudaStream_t st);
 
 // fp32 (CUDA-core) contractions with fused epilogues
 void launch_simt_forward(const Step& s, cudaStream_t st);
-void launch_simt_backward(const Step& s, cudaStream_t st);   // G'' + q_part, dW, dx_part
+void launch_simt_bwdg(const Step& s, cudaStream_t st);   // recompute S -> G'' + q_part
+void launch_simt_dw(const Step& s, cudaStream_t st);
+void launch_simt_dx(const Step& s, cudaStream_t st);
 int simt_forward_tiles(int C);                               // NT for the fp32 path
 int simt_dx_splits(int B, int D, int Cp);
 
@@ -81,7 +83,11 @@ int umma_forward_tiles(int Cp);
 int umma_dx_splits(int B, int D, int Cp, int num_sms);
 void launch_umma_forward(const Step& s, const UmmaMaps& m, const UmmaTuning& tu, int num_sms,
                          cudaStream_t st);
-void launch_umma_backward(const Step& s, const UmmaMaps& m, const UmmaTuning& tu, int num_sms,
-                          cudaStream_t st);
+void launch_umma_bwdg(const Step& s, const UmmaMaps& m, const UmmaTuning& tu, int num_sms,
+                      cudaStream_t st);
+void launch_umma_dw(const Step& s, const UmmaMaps& m, const UmmaTuning& tu, int num_sms,
+                    cudaStream_t st);
+void launch_umma_dx(const Step& s, const UmmaMaps& m, const UmmaTuning& tu, int num_sms,
+                    cudaStream_t st);
 
 }  // namespace asmh

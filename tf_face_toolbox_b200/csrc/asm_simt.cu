@@ -281,11 +281,17 @@ void launch_simt_forward(const Step& s, cudaStream_t st) {
   simt_kernel<K_FWD><<<grd, 256, 0, st>>>(s, 0);
 }
 
-void launch_simt_backward(const Step& s, cudaStream_t st) {
+void launch_simt_bwdg(const Step& s, cudaStream_t st) {
   dim3 g1((s.Cp + BN - 1) / BN, (s.B + BM - 1) / BM);
   simt_kernel<K_BWDG><<<g1, 256, 0, st>>>(s, 0);
+}
+
+void launch_simt_dw(const Step& s, cudaStream_t st) {
   dim3 g2((s.C + BN - 1) / BN, (s.D + BM - 1) / BM);
   simt_kernel<K_DW><<<g2, 256, 0, st>>>(s, 0);
+}
+
+void launch_simt_dx(const Step& s, cudaStream_t st) {
   int kper = (s.C + s.KS - 1) / s.KS;
   kper = (kper + BK - 1) / BK * BK;
   dim3 g3((s.D + BN - 1) / BN, (s.B + BM - 1) / BM, s.KS);

@@ -459,23 +459,29 @@ void launch_umma_forward(const Step& s, const UmmaMaps& m, const UmmaTuning& tu,
   umma_kernel<U_FWD><<<min(total, num_sms), 256, SMEM_BYTES, st>>>(m.xb_k, m.wb_mn, s, g);
 }
 
-void launch_umma_backward(const Step& s, const UmmaMaps& m, const UmmaTuning& tu, int num_sms,
-                          cudaStream_t st) {
-  UmmaArgs g = base_args(tu);
-  // recompute S -> G'' (bf16) + q_part
+void launch_umma_bwdg(const Step& s, const UmmaMaps& m, const UmmaTuning& tu, int num_sms,
+                      cudaStream_t st) {
+  UmmaArgs g = base_args(tu);   // recompute S -> G'' (bf16) + q_part
   g.mt = (s.B + BM - 1) / BM;
   g.nt = s.Cp / BN;
   g.kb_total = (s.D + BK - 1) / BK;
   g.kb_per = g.kb_total;
   umma_kernel<U_BWDG><<<min(g.mt * g.nt, num_sms), 256, SMEM_BYTES, st>>>(m.xb_k, m.wb_mn, s, g);
-  launch_dw_coef(s, st);
-  // dW = Xb^T G'' - Wb * coef
+}
+
+void launch_umma_dw(const Step& s, const UmmaMaps& m, const UmmaTuning& tu, int num_sms,
+                    cudaStream_t st) {
+  UmmaArgs g = base_args(tu);   // dW = Xb^T G'' - Wb * coef
   g.mt = (s.D + BM - 1) / BM;
   g.nt = s.Cp / BN;
   g.kb_total = (s.B + BK - 1) / BK;
   g.kb_per = g.kb_total;
   umma_kernel<U_DW><<<min(g.mt * g.nt, num_sms), 256, SMEM_BYTES, st>>>(m.xb_mn, m.g_mn, s, g);
-  // dX partials = G'' Wb^T, split over the classes
+}
+
+void launch_umma_dx(const Step& s, const UmmaMaps& m, const UmmaTuning& tu, int num_sms,
+                    cudaStream_t st) {
+  UmmaArgs g = base_args(tu);   // dX partials = G'' Wb^T, split over the classes
   g.mt = (s.B + BM - 1) / BM;
   g.nt = (s.D + BN - 1) / BN;
   g.kb_total = (s.Cp + BK - 1) / BK;
