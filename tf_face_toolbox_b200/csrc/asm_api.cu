@@ -25,7 +25,7 @@ struct asm_head {
   size_t dx_part_capacity = 0;   // floats
   UmmaMaps maps{};
   int maps_B = -1;
-  UmmaTuning tune{8192, 1024, 2048};
+  UmmaTuning tune{8192, 1024, 2048, 0};
   bool fwd_valid = false;
   int launches = 0;
   // optional per-kernel timing (asm_set_profiling): event i is recorded before kernel i
@@ -43,8 +43,8 @@ thread_local char g_create_err[512] = "";
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct Layout {
-  size_t ylocal, flags, n, inv_n, inv_c, tgt_s, tgt_f, part, stats_local, lse, gtarget, rcoef,
-      q_part, coef, G, dx_part, Xb, Wb, total;
+  size_t ylocal, flags, n, inv_n, inv_c, tgt_s, tgt_f, part, stats_local, lse, negoff, gtarget, rcoef,
+      q_part, G, dx_part, Xb, Wb, total;
   int Cp, NT, MT;
   size_t dx_capacity;
 };
@@ -67,7 +67,7 @@ Layout make_layout(const asm_config& c, int num_sms) {
   const size_t B = c.B_max, D = c.D;
   L.Cp = (int)align_up(c.C_local, 256);
   L.NT = (L.Cp + 127) / 128;
-  L.MT = (int)((B + kRowTileHost - 1) / kRowTileHost);
+  L.MT = 2 * (int)((B + 255) / 256);      // >= ceil(B/128): covers both paths
   // dX split-K partial capacity: the larger of both paths at B_max, but never less than
   // what a single 128-row tile would use (KS grows when B shrinks).
   const int ks_simt = simt_dx_splits(c.B_max, c.D, L.Cp);
@@ -89,10 +89,10 @@ Layout make_layout(const asm_config& c, int num_sms) {
   L.part = take(B * (size_t)L.NT * 8);
   L.stats_local = take(3 * B * 4);
   L.lse = take(B * 4);
+  L.negoff = take(B * 4);
   L.gtarget = take(B * 4);
   L.rcoef = take(B * 4);
   L.q_part = take((size_t)L.MT * L.Cp * 4);
-  L.coef = take((size_t)L.Cp * 4);
   L.G = take(B * (size_t)L.Cp * (c.mode == ASM_MODE_BF16 ? 2 : 4));
   L.dx_part = take(L.dx_capacity * 4);
   if (c.mode == ASM_MODE_BF16) {
@@ -153,7 +153,7 @@ int run_forward(asm_head* h, const float* X, int B, const void* labels, int labe
   s.X = X;
   s.W = W;
   s.logits = logits;
-  s.MT = (B + kRowTileHost - 1) / kRowTileHost;
+  s.MT = h->cfg.mode == ASM_MODE_BF16 ? umma_q_parts(B) : (B + kRowTileHost - 1) / kRowTileHost;
   h->launches = 0;
   h->n_marks = 0;
   h->fwd_valid = false;
@@ -197,8 +197,6 @@ int run_backward(asm_head* h, const float* stats_all, int n_shards, float* loss_
     mark(h, "bwd_recompute_g", stream);
     if (tc) launch_umma_bwdg(s, h->maps, h->tune, h->num_sms, stream);
     else launch_simt_bwdg(s, stream);
-    mark(h, "dw_coef", stream);
-    launch_dw_coef(s, stream);
     mark(h, "dw_gemm", stream);
     if (tc) launch_umma_dw(s, h->maps, h->tune, h->num_sms, stream);
     else launch_simt_dw(s, stream);
@@ -253,6 +251,7 @@ int asm_create(asm_head** out, const asm_config* cfg) {
   if ((e = getenv("ASM_UMMA_MN_LBO"))) h->tune.mn_lbo = (uint32_t)atoi(e);
   if ((e = getenv("ASM_UMMA_MN_SBO"))) h->tune.mn_sbo = (uint32_t)atoi(e);
   if ((e = getenv("ASM_UMMA_MN_KSTEP"))) h->tune.mn_kstep = (uint32_t)atoi(e);
+  if ((e = getenv("ASM_UMMA_DEBUG"))) h->tune.debug_flags = (uint32_t)atoi(e);
   const Layout L = make_layout(*cfg, h->num_sms);
   cudaError_t ce = cudaMalloc(&h->ws, L.total);
   if (ce != cudaSuccess) {
@@ -290,10 +289,10 @@ int asm_create(asm_head** out, const asm_config* cfg) {
   s.part = (float2*)(w + L.part);
   s.stats_local = (float*)(w + L.stats_local);
   s.lse = (float*)(w + L.lse);
+  s.negoff = (float*)(w + L.negoff);
   s.gtarget = (float*)(w + L.gtarget);
   s.rcoef = (float*)(w + L.rcoef);
   s.q_part = (float*)(w + L.q_part);
-  s.coef = (float*)(w + L.coef);
   s.G = (void*)(w + L.G);
   s.dx_part = (float*)(w + L.dx_part);
   h->dx_part_capacity = L.dx_capacity;

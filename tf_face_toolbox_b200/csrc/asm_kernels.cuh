@@ -33,11 +33,11 @@ struct Step {
   int NT;                    // number of column tiles of the forward kernel
   float* stats_local;        // [3, B]
   float* lse;                // [B]   M_i + log Z_i (global)
+  float* negoff;             // [B]   -(lse_i * log2 e) + log2(1/B): exp2 offset of the backward
   float* gtarget;            // [B]   G'_{i,y_i}
   float* rcoef;              // [B]   r_i  (0 if not owned)
-  float* q_part;             // [MT, Cp] column sums  sum_i G'_ij s_ij per 128-row tile
+  float* q_part;             // [MT, Cp] column sums  sum_i G'_ij s_ij per 128-row group
   int MT;
-  float* coef;               // [Cp]  q_j / c_j^2  (dW normalisation-Jacobian correction)
   void* G;                   // [B, Cp]  G'' = G' * inv_c   (fp32 or bf16 by mode)
   float* dx_part;            // [KS, B, D] split-K partials of dX
   int KS;
@@ -62,24 +62,24 @@ void launch_simt_dx(const Step& s, cudaStream_t st);
 int simt_forward_tiles(int C);                               // NT for the fp32 path
 int simt_dx_splits(int B, int D, int Cp);
 
-// q_part -> coef[j] = (sum_t q_part[t][j]) * inv_c[j]^2
-void launch_dw_coef(const Step& s, cudaStream_t st);
-
 // bf16 (tcgen05 / TMEM / TMA) contractions with fused epilogues
 struct UmmaMaps {            // TMA descriptors over the bf16 workspace operands
-  CUtensorMap xb_k, xb_mn, wb_mn, wb_k, g_k, g_mn;
+  CUtensorMap xb_k, xb_k256, xb_mn, wb_mn, wb_k, g_k, g_mn;
 };
 struct UmmaTuning {          // MN-major shared-memory descriptor parameters (bytes)
   uint32_t mn_lbo, mn_sbo, mn_kstep;
+  uint32_t debug_flags;      // bit0: skip epilogue math (ASM_UMMA_DEBUG, bring-up only)
 };
 struct UmmaArgs {
   int mt, nt, ks, kb_total, kb_per;
   uint64_t desc_hi_k, desc_hi_mn;
   uint32_t kstep_mn;
+  uint32_t debug_flags;
 };
 cudaError_t umma_configure();
 bool umma_build_maps(UmmaMaps* m, const Step& s);
 int umma_forward_tiles(int Cp);
+int umma_q_parts(int B);
 int umma_dx_splits(int B, int D, int Cp, int num_sms);
 void launch_umma_forward(const Step& s, const UmmaMaps& m, const UmmaTuning& tu, int num_sms,
                          cudaStream_t st);

@@ -27,24 +27,38 @@ __global__ void __launch_bounds__(256) prep_kernel(Step s, const void* labels, i
       const bool v0 = j0 < s.C, v1 = j0 + 1 < s.C;
       const float* w = s.W + j0;
       __nv_bfloat16* wb = BF16 ? s.Wb + j0 : nullptr;
-#pragma unroll 8
-      for (int d = ty; d < s.D; d += 8) {
-        float x0 = 0.f, x1 = 0.f;
-        if (VEC2) {
-          if (v1) {
-            const float2 v = __ldg(reinterpret_cast<const float2*>(w + (size_t)d * s.C));
-            x0 = v.x; x1 = v.y;
-          } else if (v0) {
-            x0 = __ldg(w + (size_t)d * s.C);
+      // U rows per trip: all loads are issued before the first use so that U x 8 B per
+      // thread are in flight (the bf16 stores would otherwise serialise the loads).
+      constexpr int U = 16;
+      for (int d0 = ty; d0 < s.D; d0 += 8 * U) {
+        float x0[U], x1[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int d = d0 + 8 * u;
+          x0[u] = 0.f; x1[u] = 0.f;
+          if (d < s.D) {
+            if (VEC2) {
+              if (v1) {
+                const float2 v = __ldg(reinterpret_cast<const float2*>(w + (size_t)d * s.C));
+                x0[u] = v.x; x1[u] = v.y;
+              } else if (v0) {
+                x0[u] = __ldg(w + (size_t)d * s.C);
+              }
+            } else {
+              if (v0) x0[u] = __ldg(w + (size_t)d * s.C);
+              if (v1) x1[u] = __ldg(w + (size_t)d * s.C + 1);
+            }
           }
-        } else {
-          if (v0) x0 = __ldg(w + (size_t)d * s.C);
-          if (v1) x1 = __ldg(w + (size_t)d * s.C + 1);
         }
-        a0 = fmaf(x0, x0, a0);
-        a1 = fmaf(x1, x1, a1);
-        if (BF16)
-          *reinterpret_cast<__nv_bfloat162*>(wb + (size_t)d * s.Cp) = __floats2bfloat162_rn(x0, x1);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int d = d0 + 8 * u;
+          a0 = fmaf(x0[u], x0[u], a0);
+          a1 = fmaf(x1[u], x1[u], a1);
+          if (BF16 && d < s.D)
+            *reinterpret_cast<__nv_bfloat162*>(wb + (size_t)d * s.Cp) =
+                __floats2bfloat162_rn(x0[u], x1[u]);
+        }
       }
     }
     red[ty][tx * 2] = a0;
@@ -152,6 +166,7 @@ __global__ void __launch_bounds__(1024) combine_global_kernel(Step s, const floa
     }
     const float lse = M + logf(Z);
     s.lse[row] = lse;
+    s.negoff[row] = -lse * 1.4426950408889634f + log2f(s.invB);
     acc += lse - fy;
     float gt = 0.f, r = 0.f;
     if (s.ylocal[row] >= 0) {
@@ -179,22 +194,6 @@ __global__ void __launch_bounds__(1024) combine_global_kernel(Step s, const floa
 
 void launch_combine_global(const Step& s, const float* stats_all, int n_shards, cudaStream_t st) {
   combine_global_kernel<<<1, 1024, 0, st>>>(s, stats_all, n_shards);
-}
-
-// ---------------------------------------------------------------------------------------
-// dw_coef: coef[j] = (sum over row tiles of q_part[t][j]) / c_j^2
-// ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) dw_coef_kernel(Step s) {
-  const int j = blockIdx.x * 256 + threadIdx.x;
-  if (j >= s.Cp) return;
-  float q = 0.f;
-  for (int t = 0; t < s.MT; ++t) q += s.q_part[(size_t)t * s.Cp + j];
-  const float ic = s.inv_c[j];
-  s.coef[j] = q * ic * ic;
-}
-
-void launch_dw_coef(const Step& s, cudaStream_t st) {
-  dw_coef_kernel<<<(s.Cp + 255) / 256, 256, 0, st>>>(s);
 }
 
 // ---------------------------------------------------------------------------------------

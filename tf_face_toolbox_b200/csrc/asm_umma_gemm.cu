@@ -3,17 +3,23 @@
 //
 // One persistent, warp-specialised kernel template (CTA tile 128 x 256 x 64, 4-stage
 // TMA->smem ring, 2 accumulator stages of 256 TMEM columns so the epilogue of tile t
-// overlaps the MMAs of tile t+1):
+// overlaps the MMAs of tile t+1), 384 threads:
 //   warp 0  : TMA producer (one elected lane)      warp 1 : tcgen05.mma issuer (one lane)
-//   warp 2  : TMEM allocator                       warps 4-7 : epilogue, one TMEM lane each
+//   warp 2  : TMEM allocator                       warps 4-11 : epilogue; warp w owns TMEM
+//             lanes 32*(w%4).. and the column half (w-4)/4 of the 256-column accumulator
 //
-//   KIND        D[MxN]                 A (M x K)                 B (N x K)
-//   FWD / BWDG  S  [B x C]    K = D    Xb [B,D]   K-major        Wb [D,Cp]  MN-major
-//   DW          dW [D x C]    K = B    Xb [B,D]   MN-major       G''[B,Cp]  MN-major
-//   DX          dX [B x D]    K = C    G''[B,Cp]  K-major        Wb [D,Cp]  K-major (split-K)
-// so the bf16 copy of W keeps the reference's [D, C] orientation (no transpose anywhere),
-// every operand is read by TMA with 128-byte swizzle, and nothing but [B]-sized statistics
-// leaves the forward kernel.
+//   KIND   D (lanes x columns)          A (M x K)                  B (N x K)
+//   FWD    S   [batch x classes] K=D    Xb [B,D]   K-major         Wb [D,Cp]  MN-major
+//   BWDG   S^T [classes x batch] K=D    Wb [D,Cp]  MN-major        Xb [B,D]   K-major
+//   DW     dW^T[classes x d]     K=B    G''[B,Cp]  MN-major        Xb [B,D]   MN-major
+//   DX     dX  [batch x d]       K=C    G''[B,Cp]  K-major         Wb [D,Cp]  K-major (split-K)
+// The orientation is chosen per kernel so that every reduction is thread-local and every
+// global store is coalesced: in FWD a thread owns a batch row (online max / sum-exp over the
+// classes in its registers); in BWDG and DW a thread owns a class (the column sums q_j and
+// the 1/c_j scaling are per-thread constants, and for a fixed batch row / fixed d the 32
+// lanes of a warp write 32 consecutive classes of G'' / dW).  The bf16 copy of W keeps the
+// reference's [D, C] orientation (no transpose anywhere), every operand is read by TMA with
+// 128-byte swizzle, and nothing but [B]-sized statistics leaves the forward kernel.
 #include "asm_common.cuh"
 #include "asm_kernels.cuh"
 #include "asm_umma.cuh"
@@ -26,8 +32,11 @@ constexpr int A_BYTES = BM * BK * 2;           // 16 KB
 constexpr int B_BYTES = BN * BK * 2;           // 32 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES; // 48 KB
 constexpr int CHUNK_BYTES = 64 * BK * 2;       // one 64-wide MN-major chunk: 8 KB
-constexpr int AUX_BYTES = 256 + 4 * BN * 4;    // barriers + tmem ptr, column-sum scratch
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + AUX_BYTES + 1024;
+constexpr int NUM_THREADS = 384;
+constexpr int EPI_THREADS = 256;
+constexpr int AUX_BARS = 256;                  // barriers + tmem ptr
+constexpr int AUX_VEC = 3 * 2 * BN * 4;        // per-tile vectors: 3 arrays x 2 stages x 256
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + AUX_BARS + AUX_VEC + 1024;
 constexpr float LOG2E = 1.4426950408889634f;
 
 enum { U_FWD = 0, U_BWDG = 1, U_DW = 2, U_DX = 3 };
@@ -35,18 +44,32 @@ enum { U_FWD = 0, U_BWDG = 1, U_DW = 2, U_DX = 3 };
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
-__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&v);
+__device__ __forceinline__ float fast_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void st_bf16(__nv_bfloat16* p, float v) {
+  *p = __float2bfloat16_rn(v);
+}
+// Rare paths of the forward epilogue, kept out of line so the hot loop stays small.
+__device__ __noinline__ float fwd_target(float* tgt_s, float* tgt_f, const float* n,
+                                         const float* inv_n, int m, float lambda, int row,
+                                         float sv) {
+  tgt_s[row] = sv;
+  const float fv = target_logit(sv, n[row], inv_n[row], m, lambda);
+  tgt_f[row] = fv;
+  return fv;
 }
 }  // namespace
 
 template <int KIND>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(NUM_THREADS, 1)
 umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
             Step s, UmmaArgs g) {
-  constexpr bool A_MN = (KIND == U_DW);
-  constexpr bool B_MN = (KIND != U_DX);
+  constexpr bool A_MN = (KIND == U_BWDG || KIND == U_DW);
+  constexpr bool B_MN = (KIND == U_FWD || KIND == U_DW);
+  constexpr bool N_FAST = (KIND == U_BWDG || KIND == U_DW);   // tile order: n index fastest
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -55,7 +78,9 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
   uint64_t* tfull = empty + STAGES;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
-  float* colsum = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256);  // [4][BN]
+  float* vec0 = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + AUX_BARS);  // [2][BN]
+  float* vec1 = vec0 + 2 * BN;
+  float* vec2 = vec1 + 2 * BN;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -70,7 +95,7 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&tfull[a], 1);
-      ptx::mbar_init(&tempty[a], 128);
+      ptx::mbar_init(&tempty[a], EPI_THREADS);
     }
     ptx::fence_barrier_init();
   }
@@ -85,14 +110,20 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
 
   const int tiles_mn = g.mt * g.nt;
   const int total = tiles_mn * g.ks;
+  auto decode = [&](int u, int& z, int& m_idx, int& n_idx) {
+    z = u / tiles_mn;
+    const int t = u - z * tiles_mn;
+    if (N_FAST) { m_idx = t / g.nt; n_idx = t - m_idx * g.nt; }
+    else        { n_idx = t / g.mt; m_idx = t - n_idx * g.mt; }
+  };
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     if (ptx::elect_one()) {
       uint32_t it = 0;
       for (int u = blockIdx.x; u < total; u += gridDim.x) {
-        const int z = u / tiles_mn, t = u - z * tiles_mn;
-        const int n_idx = t / g.mt, m_idx = t - n_idx * g.mt;
+        int z, m_idx, n_idx;
+        decode(u, z, m_idx, n_idx);
         const int m0 = m_idx * BM, n0 = n_idx * BN;
         const int kb0 = z * g.kb_per, kb1 = min(g.kb_total, kb0 + g.kb_per);
         for (int kb = kb0; kb < kb1; ++kb, ++it) {
@@ -155,209 +186,218 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
       }
     }
   } else if (warp >= 4) {
-    // ------------------------------------------------------------ epilogue (128 threads)
-    const int q4 = warp & 3;
-    const int row_in_tile = q4 * 32 + lane;
+    // ------------------------------------------------------------ epilogue (256 threads)
+    const int q4 = warp & 3;                  // TMEM lane quarter this warp may access
+    const int half = (warp - 4) >> 2;         // which 128 of the 256 accumulator columns
+    const int et = threadIdx.x - 128;         // 0..255
+    const int lane_row = q4 * 32 + lane;      // row of the tile owned by this thread
+    const int col0 = half * 128;
     uint32_t lt = 0;
     for (int u = blockIdx.x; u < total; u += gridDim.x, ++lt) {
-      const int z = u / tiles_mn, t = u - z * tiles_mn;
-      const int n_idx = t / g.mt, m_idx = t - n_idx * g.mt;
+      int z, m_idx, n_idx;
+      decode(u, z, m_idx, n_idx);
       const int m0 = m_idx * BM, n0 = n_idx * BN;
       const uint32_t a = lt & 1, aph = (lt >> 1) & 1;
-      ptx::mbar_wait(&tfull[a], aph);
-      ptx::tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + a * BN;
-      const int row = m0 + row_in_tile;
-      uint32_t r[32];
+      const uint32_t taddr =
+          tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + a * BN + col0;
+      float* v0 = vec0 + a * BN;
+      float* v1 = vec1 + a * BN;
+      float* v2 = vec2 + a * BN;
+      uint32_t r0[32], r1[32];
+      if (g.debug_flags & 1) {                // bring-up knob: mainloop only, no epilogue math
+        ptx::mbar_wait(&tfull[a], aph);
+        ptx::tc_fence_after();
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(&tempty[a]);
+        continue;
+      }
+
+      // The four 32-column chunks of this thread's half are read with the TMEM load of
+      // chunk c+1 in flight while chunk c is processed; the accumulator stage is released
+      // to the MMA warp as soon as the last chunk is in registers.  The chunk body is
+      // instantiated twice only (r0 / r1) to keep the kernel inside the instruction cache.
+#define ASM_EPILOGUE_CHUNKS(process)                       \
+      ptx::tmem_ld32(taddr, r0);                           \
+      _Pragma("unroll 1")                                  \
+      for (int cp = 0; cp < 2; ++cp) {                     \
+        ptx::tmem_ld_wait_dep(r0);                         \
+        ptx::tmem_ld32(taddr + cp * 64 + 32, r1);          \
+        process(r0, cp * 2);                               \
+        ptx::tmem_ld_wait_dep(r1);                         \
+        if (cp == 0) {                                     \
+          ptx::tmem_ld32(taddr + 64, r0);                  \
+        } else {                                           \
+          ptx::tc_fence_before();                          \
+          ptx::mbar_arrive(&tempty[a]);                    \
+        }                                                  \
+        process(r1, cp * 2 + 1);                           \
+      }
 
       if (KIND == U_FWD) {
+        // ---- thread = batch row, columns = classes.  Stage 1/c_j for the tile in smem.
+        v0[et] = s.inv_c[n0 + et];
+        const int row = m0 + lane_row;
         const bool rv = row < s.B;
         const int yl = rv ? s.ylocal[row] : -1;
+        const bool last_tile = n0 + BN > s.C;
+        named_bar_sync(1, EPI_THREADS);
+        ptx::mbar_wait(&tfull[a], aph);
+        ptx::tc_fence_after();
         float run_m = -INFINITY, run_z = 0.f;
-#pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-          const int jb = n0 + c * 32;
-          ptx::tmem_ld32(taddr + c * 32, r);
-          ptx::tmem_ld_wait();
+        auto process = [&](const uint32_t (&r)[32], int c) {
+          const int cb = col0 + c * 32;              // column offset inside the tile
+          const int jb = n0 + cb;
           float v[32];
 #pragma unroll
           for (int b4 = 0; b4 < 8; ++b4) {
-            const float4 ic = __ldg(reinterpret_cast<const float4*>(s.inv_c + jb) + b4);
+            const float4 ic = *reinterpret_cast<const float4*>(v0 + cb + b4 * 4);
             v[b4 * 4 + 0] = __uint_as_float(r[b4 * 4 + 0]) * ic.x;
             v[b4 * 4 + 1] = __uint_as_float(r[b4 * 4 + 1]) * ic.y;
             v[b4 * 4 + 2] = __uint_as_float(r[b4 * 4 + 2]) * ic.z;
             v[b4 * 4 + 3] = __uint_as_float(r[b4 * 4 + 3]) * ic.w;
           }
-          if (jb + 32 > s.C) {
+          // rare paths (last class tile, target column, logits requested) are kept compact
+          if (last_tile) {
 #pragma unroll
             for (int b = 0; b < 32; ++b)
               if (jb + b >= s.C) v[b] = -INFINITY;
           }
-          if (yl >= jb && yl < jb + 32) {
+          const int bsel = yl - jb;
+          if (bsel >= 0 && bsel < 32) {
+            float sv = 0.f;
 #pragma unroll
             for (int b = 0; b < 32; ++b)
-              if (jb + b == yl) {
-                s.tgt_s[row] = v[b];
-                v[b] = target_logit(v[b], s.n[row], s.inv_n[row], s.m, s.lambda);
-                s.tgt_f[row] = v[b];
-              }
-          }
-          if (s.logits && rv) {
+              if (b == bsel) sv = v[b];
+            const float fv = fwd_target(s.tgt_s, s.tgt_f, s.n, s.inv_n, s.m, s.lambda, row, sv);
 #pragma unroll
             for (int b = 0; b < 32; ++b)
-              if (jb + b < s.C) s.logits[(size_t)row * s.C + jb + b] = v[b];
+              if (b == bsel) v[b] = fv;
           }
-          float cm = v[0];
+          if (s.logits != nullptr && rv) {
+            float* dst = s.logits + (size_t)row * s.C + jb;
 #pragma unroll
-          for (int b = 1; b < 32; ++b) cm = fmaxf(cm, v[b]);
+            for (int b = 0; b < 32; ++b)
+              if (jb + b < s.C) dst[b] = v[b];
+          }
+          float cm0 = fmaxf(v[0], v[1]), cm1 = fmaxf(v[2], v[3]);
+#pragma unroll
+          for (int b = 4; b < 32; b += 2) {
+            cm0 = fmaxf(cm0, v[b]);
+            cm1 = fmaxf(cm1, v[b + 1]);
+          }
+          const float cm = fmaxf(cm0, cm1);
           if (cm > -INFINITY) {
             const float nm = fmaxf(run_m, cm);
             const float nml = nm * LOG2E;
-            float zs = 0.f;
+            float z0 = 0.f, z1 = 0.f, z2 = 0.f, z3 = 0.f;
 #pragma unroll
-            for (int b = 0; b < 32; ++b) zs += exp2f(fmaf(v[b], LOG2E, -nml));
-            run_z = run_z * exp2f((run_m - nm) * LOG2E) + zs;
+            for (int b = 0; b < 32; b += 4) {
+              z0 += fast_ex2(fmaf(v[b], LOG2E, -nml));
+              z1 += fast_ex2(fmaf(v[b + 1], LOG2E, -nml));
+              z2 += fast_ex2(fmaf(v[b + 2], LOG2E, -nml));
+              z3 += fast_ex2(fmaf(v[b + 3], LOG2E, -nml));
+            }
+            run_z = run_z * fast_ex2((run_m - nm) * LOG2E) + ((z0 + z1) + (z2 + z3));
             run_m = nm;
           }
-        }
-        ptx::tc_fence_before();
-        ptx::mbar_arrive(&tempty[a]);
-        if (rv) s.part[(size_t)row * s.NT + n_idx] = make_float2(run_m, run_z);
+        };
+        ASM_EPILOGUE_CHUNKS(process)
+        if (rv) s.part[(size_t)row * s.NT + n_idx * 2 + half] = make_float2(run_m, run_z);
       } else if (KIND == U_BWDG) {
-        const bool rv = row < s.B;
-        const int yl = rv ? s.ylocal[row] : -1;
-        const float lsel = rv ? s.lse[row] * LOG2E : INFINITY;
-        const float gt = rv ? s.gtarget[row] : 0.f;
-        __nv_bfloat16* Gw = reinterpret_cast<__nv_bfloat16*>(s.G);
-#pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-          const int jb = n0 + c * 32;
-          ptx::tmem_ld32(taddr + c * 32, r);
-          ptx::tmem_ld_wait();
-          float gq[32];   // G'' = G' / c_j
-          float pr[32];   // G' * s   (column-sum terms of q_j)
+        // ---- thread = class j (row m), columns = batch rows i.  Stage the per-row terms.
+        {
+          const int i = n0 + et;
+          const bool iv = i < s.B;
+          v0[et] = iv ? s.negoff[i] : -INFINITY;              // -(lse_i log2e) + log2(1/B)
+          v1[et] = iv ? __int_as_float(s.ylocal[i]) : __int_as_float(-1);
+          v2[et] = iv ? s.gtarget[i] : 0.f;
+        }
+        const int j = m0 + lane_row;                          // class (< Cp always)
+        const float ic = s.inv_c[j];
+        __nv_bfloat16* Gw = reinterpret_cast<__nv_bfloat16*>(s.G) + j;
+        named_bar_sync(1, EPI_THREADS);
+        ptx::mbar_wait(&tfull[a], aph);
+        ptx::tc_fence_after();
+        float q0 = 0.f, q1 = 0.f;
+        auto process = [&](const uint32_t (&r)[32], int c) {
+          const int cb = col0 + c * 32;
+          const int ib = n0 + cb;                             // first batch row of the chunk
+          const int nvalid = s.B - ib;                        // rows of this chunk inside the batch
+          __nv_bfloat16* gdst = Gw + (size_t)ib * s.Cp;
 #pragma unroll
           for (int b4 = 0; b4 < 8; ++b4) {
-            const float4 ic4 = __ldg(reinterpret_cast<const float4*>(s.inv_c + jb) + b4);
-            const float icv[4] = {ic4.x, ic4.y, ic4.z, ic4.w};
+            const float4 no = *reinterpret_cast<const float4*>(v0 + cb + b4 * 4);
+            const int4 yy = *reinterpret_cast<const int4*>(v1 + cb + b4 * 4);
+            const float nof[4] = {no.x, no.y, no.z, no.w};
+            const int yv[4] = {yy.x, yy.y, yy.z, yy.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const int b = b4 * 4 + e;
-              const float sv = __uint_as_float(r[b]) * icv[e];
-              const float gp = exp2f(fmaf(sv, LOG2E, -lsel)) * s.invB;
-              pr[b] = gp * sv;
-              gq[b] = gp * icv[e];
+              const float sv = __uint_as_float(r[b]) * ic;
+              float gp = fast_ex2(fmaf(sv, LOG2E, nof[e]));   // softmax prob / B
+              if (yv[e] == j) gp = v2[cb + b];                // target column: G'_{i,y}
+              if (e & 1) q1 = fmaf(gp, sv, q1); else q0 = fmaf(gp, sv, q0);
+              if (b < nvalid) st_bf16(gdst + (size_t)b * s.Cp, gp * ic);
             }
           }
-          if (yl >= jb && yl < jb + 32) {
-#pragma unroll
-            for (int b = 0; b < 32; ++b)
-              if (jb + b == yl) {
-                const float ic = s.inv_c[yl];
-                const float sv = __uint_as_float(r[b]) * ic;
-                pr[b] = gt * sv;
-                gq[b] = gt * ic;
-              }
-          }
-          if (rv) {
-            uint4* dst = reinterpret_cast<uint4*>(Gw + (size_t)row * s.Cp + jb);
-#pragma unroll
-            for (int v4 = 0; v4 < 4; ++v4) {
-              uint4 o;
-              o.x = pack_bf16(gq[v4 * 8 + 0], gq[v4 * 8 + 1]);
-              o.y = pack_bf16(gq[v4 * 8 + 2], gq[v4 * 8 + 3]);
-              o.z = pack_bf16(gq[v4 * 8 + 4], gq[v4 * 8 + 5]);
-              o.w = pack_bf16(gq[v4 * 8 + 6], gq[v4 * 8 + 7]);
-              dst[v4] = o;
-            }
-          }
-          // butterfly transpose-reduce: lane l ends with sum over the warp's 32 rows of
-          // column (jb + l)
-#pragma unroll
-          for (int off = 16; off >= 1; off >>= 1) {
-            const bool up = (lane & off) != 0;
-#pragma unroll
-            for (int i = 0; i < off; ++i) {
-              const float send = up ? pr[i] : pr[i + off];
-              const float keep = up ? pr[i + off] : pr[i];
-              pr[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-            }
-          }
-          colsum[q4 * BN + c * 32 + lane] = pr[0];
-        }
-        ptx::tc_fence_before();
-        ptx::mbar_arrive(&tempty[a]);
-        named_bar_sync(1, 128);
-        {
-          const int e = threadIdx.x - 128;
-#pragma unroll
-          for (int cc = e; cc < BN; cc += 128) {
-            const float q = colsum[cc] + colsum[BN + cc] + colsum[2 * BN + cc] + colsum[3 * BN + cc];
-            s.q_part[(size_t)m_idx * s.Cp + n0 + cc] = q;
-          }
-        }
-        named_bar_sync(1, 128);
+        };
+        ASM_EPILOGUE_CHUNKS(process)
+        s.q_part[(size_t)(n_idx * 2 + half) * s.Cp + j] = q0 + q1;
       } else if (KIND == U_DW) {
-        const bool rv = row < s.D;                      // row = d
-        const int vecw = (s.C % 4 == 0) ? 4 : ((s.C % 2 == 0) ? 2 : 1);
-#pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-          const int jb = n0 + c * 32;
-          ptx::tmem_ld32(taddr + c * 32, r);
-          ptx::tmem_ld_wait();
-          if (!rv || jb >= s.C) continue;
+        // ---- thread = class j, columns = d.  dW[d][j] = acc - Wb[d][j] * q_j / c_j^2
+        // The bf16 weights of chunk c+1 are fetched while chunk c is written.
+        const int j = m0 + lane_row;
+        const bool jv = j < s.C;
+        const int d_first = n0 + col0;
+        const unsigned short* wsrc =
+            reinterpret_cast<const unsigned short*>(s.Wb) + (size_t)d_first * s.Cp + j;
+        unsigned short wq[32];
+        auto fetch_w = [&](int c) {
+          if (d_first + c * 32 < s.D) {                       // D % 32 == 0 in bf16 mode
+#pragma unroll
+            for (int b = 0; b < 32; ++b) wq[b] = __ldg(wsrc + (size_t)(c * 32 + b) * s.Cp);
+          }
+        };
+        fetch_w(0);
+        float coef = 0.f;
+        for (int t = 0; t < s.MT; ++t) coef += s.q_part[(size_t)t * s.Cp + j];
+        const float ic = s.inv_c[j];
+        coef *= -ic * ic;
+        ptx::mbar_wait(&tfull[a], aph);
+        ptx::tc_fence_after();
+        auto process = [&](const uint32_t (&r)[32], int c) {
+          const int db = d_first + c * 32;                    // first d of the chunk
           float o[32];
-          const uint4* wsrc = reinterpret_cast<const uint4*>(s.Wb + (size_t)row * s.Cp + jb);
 #pragma unroll
-          for (int v4 = 0; v4 < 4; ++v4) {
-            const uint4 w = __ldg(wsrc + v4);
-            const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
-            const float4 c0 = __ldg(reinterpret_cast<const float4*>(s.coef + jb) + v4 * 2);
-            const float4 c1 = __ldg(reinterpret_cast<const float4*>(s.coef + jb) + v4 * 2 + 1);
-            const float cf[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+          for (int b = 0; b < 32; ++b)
+            o[b] = fmaf(__uint_as_float(static_cast<uint32_t>(wq[b]) << 16), coef,
+                        __uint_as_float(r[b]));
+          if (c < 3) fetch_w(c + 1);
+          if (jv && db < s.D) {
+            float* dst = s.dW + (size_t)db * s.C + j;
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const __nv_bfloat162 wp = *reinterpret_cast<const __nv_bfloat162*>(&ww[e]);
-              const int b = v4 * 8 + e * 2;
-              o[b] = fmaf(-__low2float(wp), cf[e * 2], __uint_as_float(r[b]));
-              o[b + 1] = fmaf(-__high2float(wp), cf[e * 2 + 1], __uint_as_float(r[b + 1]));
-            }
+            for (int b = 0; b < 32; ++b) dst[(size_t)b * s.C] = o[b];
           }
-          float* dst = s.dW + (size_t)row * s.C + jb;
-          if (jb + 32 <= s.C && vecw == 4) {
-#pragma unroll
-            for (int b = 0; b < 32; b += 4)
-              *reinterpret_cast<float4*>(dst + b) = make_float4(o[b], o[b + 1], o[b + 2], o[b + 3]);
-          } else if (jb + 32 <= s.C && vecw == 2) {
-#pragma unroll
-            for (int b = 0; b < 32; b += 2)
-              *reinterpret_cast<float2*>(dst + b) = make_float2(o[b], o[b + 1]);
-          } else {
-#pragma unroll
-            for (int b = 0; b < 32; ++b)
-              if (jb + b < s.C) dst[b] = o[b];
-          }
-        }
-        ptx::tc_fence_before();
-        ptx::mbar_arrive(&tempty[a]);
-      } else {  // U_DX
+        };
+        ASM_EPILOGUE_CHUNKS(process)
+      } else {  // U_DX: thread = batch row, columns = d; split-K partial
+        const int row = m0 + lane_row;
         const bool rv = row < s.B;
-        float* out = s.dx_part + ((size_t)z * s.B + row) * s.D + n0;
-#pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-          ptx::tmem_ld32(taddr + c * 32, r);
-          ptx::tmem_ld_wait();
-          if (rv && n0 + c * 32 < s.D) {
+        float* out = s.dx_part + ((size_t)z * s.B + row) * s.D + n0 + col0;
+        ptx::mbar_wait(&tfull[a], aph);
+        ptx::tc_fence_after();
+        auto process = [&](const uint32_t (&r)[32], int c) {
+          if (rv && n0 + col0 + c * 32 < s.D) {
 #pragma unroll
             for (int b = 0; b < 32; b += 4)
               *reinterpret_cast<float4*>(out + c * 32 + b) =
                   make_float4(__uint_as_float(r[b]), __uint_as_float(r[b + 1]),
                               __uint_as_float(r[b + 2]), __uint_as_float(r[b + 3]));
           }
-        }
-        ptx::tc_fence_before();
-        ptx::mbar_arrive(&tempty[a]);
+        };
+        ASM_EPILOGUE_CHUNKS(process)
       }
+#undef ASM_EPILOGUE_CHUNKS
     }
   }
 
@@ -402,7 +442,8 @@ bool encode_map(CUtensorMap* m, const void* base, uint64_t inner, uint64_t outer
 }
 }  // namespace
 
-int umma_forward_tiles(int Cp) { return (Cp + BN - 1) / BN; }
+int umma_forward_tiles(int Cp) { return 2 * ((Cp + BN - 1) / BN); }   // 128-class partials
+int umma_q_parts(int B) { return 2 * ((B + BN - 1) / BN); }            // 128-row partials
 
 int umma_dx_splits(int B, int D, int Cp, int num_sms) {
   const int tiles = ((B + BM - 1) / BM) * ((D + BN - 1) / BN);
@@ -417,14 +458,15 @@ int umma_dx_splits(int B, int D, int Cp, int num_sms) {
 bool umma_build_maps(UmmaMaps* m, const Step& s) {
   bool ok = true;
   // Xb [B, D]
-  ok &= encode_map(&m->xb_k, s.Xb, s.D, s.B, s.D, 64, 128);    // A of FWD/BWDG (K-major)
-  ok &= encode_map(&m->xb_mn, s.Xb, s.D, s.B, s.D, 64, 64);    // A of DW (MN-major chunks)
+  ok &= encode_map(&m->xb_k, s.Xb, s.D, s.B, s.D, 64, 128);     // A of FWD  (K-major, M = batch)
+  ok &= encode_map(&m->xb_k256, s.Xb, s.D, s.B, s.D, 64, 256);  // B of BWDG (K-major, N = batch)
+  ok &= encode_map(&m->xb_mn, s.Xb, s.D, s.B, s.D, 64, 64);     // B of DW   (MN-major, N = d)
   // Wb [D, Cp]
-  ok &= encode_map(&m->wb_mn, s.Wb, s.Cp, s.D, s.Cp, 64, 64);  // B of FWD/BWDG (MN-major)
-  ok &= encode_map(&m->wb_k, s.Wb, s.Cp, s.D, s.Cp, 64, 256);  // B of DX (K-major)
+  ok &= encode_map(&m->wb_mn, s.Wb, s.Cp, s.D, s.Cp, 64, 64);   // B of FWD / A of BWDG (MN-major)
+  ok &= encode_map(&m->wb_k, s.Wb, s.Cp, s.D, s.Cp, 64, 256);   // B of DX   (K-major, N = d)
   // G'' [B, Cp]
-  ok &= encode_map(&m->g_k, s.G, s.Cp, s.B, s.Cp, 64, 128);    // A of DX (K-major)
-  ok &= encode_map(&m->g_mn, s.G, s.Cp, s.B, s.Cp, 64, 64);    // B of DW (MN-major)
+  ok &= encode_map(&m->g_k, s.G, s.Cp, s.B, s.Cp, 64, 128);     // A of DX   (K-major, M = batch)
+  ok &= encode_map(&m->g_mn, s.G, s.Cp, s.B, s.Cp, 64, 64);     // A of DW   (MN-major, M = class)
   return ok;
 }
 
@@ -433,6 +475,7 @@ static UmmaArgs base_args(const UmmaTuning& tu) {
   g.desc_hi_k = ptx::make_smem_desc_hi(16, 1024);
   g.desc_hi_mn = ptx::make_smem_desc_hi(tu.mn_lbo, tu.mn_sbo);
   g.kstep_mn = tu.mn_kstep;
+  g.debug_flags = tu.debug_flags;
   g.ks = 1;
   return g;
 }
@@ -450,33 +493,33 @@ cudaError_t umma_configure() {
 
 void launch_umma_forward(const Step& s, const UmmaMaps& m, const UmmaTuning& tu, int num_sms,
                          cudaStream_t st) {
-  UmmaArgs g = base_args(tu);
+  UmmaArgs g = base_args(tu);   // S = Xb Wb: lanes = batch rows, columns = classes
   g.mt = (s.B + BM - 1) / BM;
   g.nt = s.Cp / BN;
   g.kb_total = (s.D + BK - 1) / BK;
   g.kb_per = g.kb_total;
   const int total = g.mt * g.nt;
-  umma_kernel<U_FWD><<<min(total, num_sms), 256, SMEM_BYTES, st>>>(m.xb_k, m.wb_mn, s, g);
+  umma_kernel<U_FWD><<<min(total, num_sms), NUM_THREADS, SMEM_BYTES, st>>>(m.xb_k, m.wb_mn, s, g);
 }
 
 void launch_umma_bwdg(const Step& s, const UmmaMaps& m, const UmmaTuning& tu, int num_sms,
                       cudaStream_t st) {
-  UmmaArgs g = base_args(tu);   // recompute S -> G'' (bf16) + q_part
-  g.mt = (s.B + BM - 1) / BM;
-  g.nt = s.Cp / BN;
+  UmmaArgs g = base_args(tu);   // recompute S^T -> G'' (bf16) + q_part: lanes = classes
+  g.mt = s.Cp / BM;
+  g.nt = (s.B + BN - 1) / BN;
   g.kb_total = (s.D + BK - 1) / BK;
   g.kb_per = g.kb_total;
-  umma_kernel<U_BWDG><<<min(g.mt * g.nt, num_sms), 256, SMEM_BYTES, st>>>(m.xb_k, m.wb_mn, s, g);
+  umma_kernel<U_BWDG><<<min(g.mt * g.nt, num_sms), NUM_THREADS, SMEM_BYTES, st>>>(m.wb_mn, m.xb_k256, s, g);
 }
 
 void launch_umma_dw(const Step& s, const UmmaMaps& m, const UmmaTuning& tu, int num_sms,
                     cudaStream_t st) {
-  UmmaArgs g = base_args(tu);   // dW = Xb^T G'' - Wb * coef
-  g.mt = (s.D + BM - 1) / BM;
-  g.nt = s.Cp / BN;
+  UmmaArgs g = base_args(tu);   // dW^T = G''^T Xb - correction: lanes = classes, columns = d
+  g.mt = s.Cp / BM;
+  g.nt = (s.D + BN - 1) / BN;
   g.kb_total = (s.B + BK - 1) / BK;
   g.kb_per = g.kb_total;
-  umma_kernel<U_DW><<<min(g.mt * g.nt, num_sms), 256, SMEM_BYTES, st>>>(m.xb_mn, m.g_mn, s, g);
+  umma_kernel<U_DW><<<min(g.mt * g.nt, num_sms), NUM_THREADS, SMEM_BYTES, st>>>(m.g_mn, m.xb_mn, s, g);
 }
 
 void launch_umma_dx(const Step& s, const UmmaMaps& m, const UmmaTuning& tu, int num_sms,
@@ -487,7 +530,7 @@ void launch_umma_dx(const Step& s, const UmmaMaps& m, const UmmaTuning& tu, int 
   g.kb_total = (s.Cp + BK - 1) / BK;
   g.ks = s.KS;
   g.kb_per = (g.kb_total + g.ks - 1) / g.ks;
-  umma_kernel<U_DX><<<min(g.mt * g.nt * g.ks, num_sms), 256, SMEM_BYTES, st>>>(m.g_k, m.wb_k, s, g);
+  umma_kernel<U_DX><<<min(g.mt * g.nt * g.ks, num_sms), NUM_THREADS, SMEM_BYTES, st>>>(m.g_k, m.wb_k, s, g);
 }
 
 }  // namespace asmh
