@@ -5,6 +5,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 
 namespace asmh {
 namespace ptx {
@@ -60,7 +61,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(addr, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(addr, parity)) {
-    if (clock64() - t0 > 4000000000ll) __trap();
+    if (clock64() - t0 > 4000000000ll) {
+      printf("asoftmax_b200: mbarrier timeout block %d thread %d smem 0x%x parity %u\n",
+             (int)blockIdx.x, (int)threadIdx.x, addr, parity);
+      __trap();
+    }
   }
 }
 

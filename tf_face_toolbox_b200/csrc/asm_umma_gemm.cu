@@ -52,6 +52,14 @@ __device__ __forceinline__ float fast_ex2(float x) {
 __device__ __forceinline__ void st_bf16(__nv_bfloat16* p, float v) {
   *p = __float2bfloat16_rn(v);
 }
+// (i == k) ? a : b as one setp + selp (keeps dynamic-index selects out of branch trees)
+__device__ __forceinline__ float sel_eq(int i, int k, float a, float b) {
+  float r;
+  asm("{\n\t.reg .pred p;\n\tsetp.eq.s32 p, %1, %2;\n\tselp.f32 %0, %3, %4, p;\n\t}\n"
+      : "=f"(r)
+      : "r"(i), "r"(k), "f"(a), "f"(b));
+  return r;
+}
 // Rare paths of the forward epilogue, kept out of line so the hot loop stays small.
 __device__ __noinline__ float fwd_target(float* tgt_s, float* tgt_f, const float* n,
                                          const float* inv_n, int m, float lambda, int row,
@@ -71,8 +79,9 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
   constexpr bool B_MN = (KIND == U_FWD || KIND == U_DW);
   constexpr bool N_FAST = (KIND == U_BWDG || KIND == U_DW);   // tile order: n index fastest
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
+  // align to 1024 B (SWIZZLE_128B atoms) by adding an integer offset, so that the compiler
+  // keeps the shared address space (ld.shared, not generic loads) for everything below
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
   uint64_t* empty = full + STAGES;
   uint64_t* tfull = empty + STAGES;
@@ -193,6 +202,37 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
     const int lane_row = q4 * 32 + lane;      // row of the tile owned by this thread
     const int col0 = half * 128;
     uint32_t lt = 0;
+    // per-tile vectors are fetched one tile ahead into registers (pre0..2) and published to
+    // shared memory at the start of their tile, so no global-load latency is exposed
+    float pre0 = 0.f, pre1 = 0.f, pre2 = 0.f;
+    auto prefetch_tile = [&](int pu) {
+      if (pu >= total) return;
+      int pz, pm, pn;
+      decode(pu, pz, pm, pn);
+      if (KIND == U_FWD) pre0 = s.inv_c[pn * BN + et];
+      if (KIND == U_BWDG) {
+        const int i = pn * BN + et;
+        const bool iv = i < s.B;
+        pre0 = iv ? s.negoff[i] : -INFINITY;                  // -(lse_i log2e) + log2(1/B)
+        pre1 = iv ? __int_as_float(s.ylocal[i]) : __int_as_float(-1);
+        pre2 = iv ? s.gtarget[i] : 0.f;
+      }
+      if (KIND == U_DW) {
+        const int pj = pm * BM + lane_row;
+        float c = 0.f;
+        for (int t = 0; t < s.MT; ++t) c += s.q_part[(size_t)t * s.Cp + pj];
+        const float pic = s.inv_c[pj];
+        pre0 = -c * pic * pic;
+        // pull the bf16 weight block of that tile [256 d x 128 classes] into L2
+        const int d = pn * BN + et;
+        if (d < s.D) {
+          const char* pw = reinterpret_cast<const char*>(s.Wb + (size_t)d * s.Cp + pm * BM);
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(pw));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(pw + 128));
+        }
+      }
+    };
+    prefetch_tile(blockIdx.x);
     for (int u = blockIdx.x; u < total; u += gridDim.x, ++lt) {
       int z, m_idx, n_idx;
       decode(u, z, m_idx, n_idx);
@@ -235,7 +275,8 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
 
       if (KIND == U_FWD) {
         // ---- thread = batch row, columns = classes.  Stage 1/c_j for the tile in smem.
-        v0[et] = s.inv_c[n0 + et];
+        v0[et] = pre0;
+        prefetch_tile(u + gridDim.x);
         const int row = m0 + lane_row;
         const bool rv = row < s.B;
         const int yl = rv ? s.ylocal[row] : -1;
@@ -263,15 +304,13 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
               if (jb + b >= s.C) v[b] = -INFINITY;
           }
           const int bsel = yl - jb;
-          if (bsel >= 0 && bsel < 32) {
+          if (bsel >= 0 && bsel < 32) {             // straight-line selects (no branch tree)
             float sv = 0.f;
 #pragma unroll
-            for (int b = 0; b < 32; ++b)
-              if (b == bsel) sv = v[b];
+            for (int b = 0; b < 32; ++b) sv = sel_eq(b, bsel, v[b], sv);
             const float fv = fwd_target(s.tgt_s, s.tgt_f, s.n, s.inv_n, s.m, s.lambda, row, sv);
 #pragma unroll
-            for (int b = 0; b < 32; ++b)
-              if (b == bsel) v[b] = fv;
+            for (int b = 0; b < 32; ++b) v[b] = sel_eq(b, bsel, fv, v[b]);
           }
           if (s.logits != nullptr && rv) {
             float* dst = s.logits + (size_t)row * s.C + jb;
@@ -305,25 +344,24 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
         if (rv) s.part[(size_t)row * s.NT + n_idx * 2 + half] = make_float2(run_m, run_z);
       } else if (KIND == U_BWDG) {
         // ---- thread = class j (row m), columns = batch rows i.  Stage the per-row terms.
-        {
-          const int i = n0 + et;
-          const bool iv = i < s.B;
-          v0[et] = iv ? s.negoff[i] : -INFINITY;              // -(lse_i log2e) + log2(1/B)
-          v1[et] = iv ? __int_as_float(s.ylocal[i]) : __int_as_float(-1);
-          v2[et] = iv ? s.gtarget[i] : 0.f;
-        }
+        v0[et] = pre0;
+        v1[et] = pre1;
+        v2[et] = pre2;
+        prefetch_tile(u + gridDim.x);
         const int j = m0 + lane_row;                          // class (< Cp always)
         const float ic = s.inv_c[j];
+        const float icl = ic * LOG2E;
         __nv_bfloat16* Gw = reinterpret_cast<__nv_bfloat16*>(s.G) + j;
         named_bar_sync(1, EPI_THREADS);
         ptx::mbar_wait(&tfull[a], aph);
         ptx::tc_fence_after();
-        float q0 = 0.f, q1 = 0.f;
+        float q0 = 0.f, q1 = 0.f;                             // sum_i G'_ij * acc_ij  (x ic later)
         auto process = [&](const uint32_t (&r)[32], int c) {
           const int cb = col0 + c * 32;
           const int ib = n0 + cb;                             // first batch row of the chunk
           const int nvalid = s.B - ib;                        // rows of this chunk inside the batch
           __nv_bfloat16* gdst = Gw + (size_t)ib * s.Cp;
+          float gq[32];
 #pragma unroll
           for (int b4 = 0; b4 < 8; ++b4) {
             const float4 no = *reinterpret_cast<const float4*>(v0 + cb + b4 * 4);
@@ -333,36 +371,44 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const int b = b4 * 4 + e;
-              const float sv = __uint_as_float(r[b]) * ic;
-              float gp = fast_ex2(fmaf(sv, LOG2E, nof[e]));   // softmax prob / B
+              const float acc = __uint_as_float(r[b]);
+              float gp = fast_ex2(fmaf(acc, icl, nof[e]));    // softmax prob / B
               if (yv[e] == j) gp = v2[cb + b];                // target column: G'_{i,y}
-              if (e & 1) q1 = fmaf(gp, sv, q1); else q0 = fmaf(gp, sv, q0);
-              if (b < nvalid) st_bf16(gdst + (size_t)b * s.Cp, gp * ic);
+              if (e & 1) q1 = fmaf(gp, acc, q1); else q0 = fmaf(gp, acc, q0);
+              gq[b] = gp * ic;
             }
+          }
+#pragma unroll
+          for (int b = 0; b < 32; ++b) {
+            if (b < nvalid) st_bf16(gdst, gq[b]);
+            gdst += s.Cp;
           }
         };
         ASM_EPILOGUE_CHUNKS(process)
-        s.q_part[(size_t)(n_idx * 2 + half) * s.Cp + j] = q0 + q1;
+        s.q_part[(size_t)(n_idx * 2 + half) * s.Cp + j] = (q0 + q1) * ic;
       } else if (KIND == U_DW) {
         // ---- thread = class j, columns = d.  dW[d][j] = acc - Wb[d][j] * q_j / c_j^2
-        // The bf16 weights of chunk c+1 are fetched while chunk c is written.
+        // coef = -q_j / c_j^2 was computed one tile ahead (and the weight block pulled into
+        // L2); the bf16 weights of chunk c+1 are fetched while chunk c is written.
         const int j = m0 + lane_row;
         const bool jv = j < s.C;
+        const float coef = pre0;
+        prefetch_tile(u + gridDim.x);
         const int d_first = n0 + col0;
         const unsigned short* wsrc =
             reinterpret_cast<const unsigned short*>(s.Wb) + (size_t)d_first * s.Cp + j;
         unsigned short wq[32];
         auto fetch_w = [&](int c) {
           if (d_first + c * 32 < s.D) {                       // D % 32 == 0 in bf16 mode
+            const unsigned short* p = wsrc + (size_t)(c * 32) * s.Cp;
 #pragma unroll
-            for (int b = 0; b < 32; ++b) wq[b] = __ldg(wsrc + (size_t)(c * 32 + b) * s.Cp);
+            for (int b = 0; b < 32; ++b) {
+              wq[b] = __ldg(p);
+              p += s.Cp;
+            }
           }
         };
         fetch_w(0);
-        float coef = 0.f;
-        for (int t = 0; t < s.MT; ++t) coef += s.q_part[(size_t)t * s.Cp + j];
-        const float ic = s.inv_c[j];
-        coef *= -ic * ic;
         ptx::mbar_wait(&tfull[a], aph);
         ptx::tc_fence_after();
         auto process = [&](const uint32_t (&r)[32], int c) {
@@ -376,7 +422,10 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
           if (jv && db < s.D) {
             float* dst = s.dW + (size_t)db * s.C + j;
 #pragma unroll
-            for (int b = 0; b < 32; ++b) dst[(size_t)b * s.C] = o[b];
+            for (int b = 0; b < 32; ++b) {
+              *dst = o[b];
+              dst += s.C;
+            }
           }
         };
         ASM_EPILOGUE_CHUNKS(process)
