@@ -43,7 +43,7 @@ thread_local char g_create_err[512] = "";
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct Layout {
-  size_t ylocal, flags, n, inv_n, inv_c, tgt_s, tgt_f, part, stats_local, lse, negoff, gtarget, rcoef,
+  size_t ylocal, flags, n, inv_n, inv_c, tgt_s, tgt_f, part, stats_local, lse, negoff, gtarget, rcoef, rowloss, counter,
       q_part, G, dx_part, Xb, Wb, total;
   int Cp, NT, MT;
   size_t dx_capacity;
@@ -67,6 +67,7 @@ Layout make_layout(const asm_config& c, int num_sms) {
   const size_t B = c.B_max, D = c.D;
   L.Cp = (int)align_up(c.C_local, 256);
   L.NT = (L.Cp + 127) / 128;
+  if (L.NT < 2 * num_sms) L.NT = 2 * num_sms;   // tcgen05 forward: 2 partials per CTA
   L.MT = 2 * (int)((B + 255) / 256);      // >= ceil(B/128): covers both paths
   // dX split-K partial capacity: the larger of both paths at B_max, but never less than
   // what a single 128-row tile would use (KS grows when B shrinks).
@@ -92,6 +93,8 @@ Layout make_layout(const asm_config& c, int num_sms) {
   L.negoff = take(B * 4);
   L.gtarget = take(B * 4);
   L.rcoef = take(B * 4);
+  L.rowloss = take(B * 4);
+  L.counter = take(256);
   L.q_part = take((size_t)L.MT * L.Cp * 4);
   L.G = take(B * (size_t)L.Cp * (c.mode == ASM_MODE_BF16 ? 2 : 4));
   L.dx_part = take(L.dx_capacity * 4);
@@ -139,7 +142,8 @@ int check_launch(asm_head* h, const char* what) {
 
 // forward half up to stats_local; shared by every entry point
 int run_forward(asm_head* h, const float* X, int B, const void* labels, int label_bytes,
-                const float* W, float lambda, float* logits, cudaStream_t stream) {
+                const float* W, float lambda, float* logits, bool want_local_stats,
+                cudaStream_t stream) {
   if (!h) return ASM_ERR_INVALID_ARG;
   if (!X || !labels || !W) return fail(h, ASM_ERR_INVALID_ARG, "null input pointer%s", "");
   if (B <= 0 || B > h->cfg.B_max) return fail(h, ASM_ERR_INVALID_ARG, "B out of range%s", "");
@@ -159,7 +163,9 @@ int run_forward(asm_head* h, const float* X, int B, const void* labels, int labe
   h->fwd_valid = false;
   CU_TRY(h, cudaMemsetAsync(s.flags, 0, 4, stream));
   if (h->cfg.mode == ASM_MODE_BF16) {
-    s.NT = umma_forward_tiles(s.Cp);
+    if ((B + 127) / 128 > h->num_sms)
+      return fail(h, ASM_ERR_INVALID_ARG, "batch too large for the tcgen05 forward grid%s", "");
+    s.NT = umma_forward_tiles(B, s.Cp, h->num_sms);
     s.KS = umma_dx_splits(B, s.D, s.Cp, h->num_sms);
     if (h->maps_B != B) {
       if (!umma_build_maps(&h->maps, s))
@@ -176,8 +182,10 @@ int run_forward(asm_head* h, const float* X, int B, const void* labels, int labe
   mark(h, "fwd_logits_stats", stream);
   if (h->cfg.mode == ASM_MODE_BF16) launch_umma_forward(s, h->maps, h->tune, h->num_sms, stream);
   else launch_simt_forward(s, stream);
-  mark(h, "combine_local", stream);
-  launch_combine_local(s, stream);
+  if (want_local_stats) {
+    mark(h, "combine_local", stream);
+    launch_combine_local(s, stream);
+  }
   mark_end(h, stream);
   int rc = check_launch(h, "forward launch");
   if (rc == ASM_OK) h->fwd_valid = true;
@@ -191,8 +199,13 @@ int run_backward(asm_head* h, const float* stats_all, int n_shards, float* loss_
   s.dX = dX;
   s.dW = dW;
   const bool tc = h->cfg.mode == ASM_MODE_BF16;
-  mark(h, "combine_global", stream);
-  launch_combine_global(s, stats_all, n_shards, stream);
+  if (stats_all) {
+    mark(h, "combine_global", stream);
+    launch_combine_global(s, stats_all, n_shards, stream);
+  } else {
+    mark(h, "combine_stats", stream);
+    launch_combine_fused(s, stream);
+  }
   if (grads) {
     mark(h, "bwd_recompute_g", stream);
     if (tc) launch_umma_bwdg(s, h->maps, h->tune, h->num_sms, stream);
@@ -292,6 +305,8 @@ int asm_create(asm_head** out, const asm_config* cfg) {
   s.negoff = (float*)(w + L.negoff);
   s.gtarget = (float*)(w + L.gtarget);
   s.rcoef = (float*)(w + L.rcoef);
+  s.rowloss = (float*)(w + L.rowloss);
+  s.counter = (unsigned int*)(w + L.counter);
   s.q_part = (float*)(w + L.q_part);
   s.G = (void*)(w + L.G);
   s.dx_part = (float*)(w + L.dx_part);
@@ -322,7 +337,7 @@ int asm_forward_partial(asm_head* h, const float* X, int32_t B, const void* labe
                         int32_t label_bytes, const float* W, float lambda, float* stats_out,
                         float* logits_out_or_null, void* cuda_stream) {
   cudaStream_t stream = (cudaStream_t)cuda_stream;
-  int rc = run_forward(h, X, B, labels, label_bytes, W, lambda, logits_out_or_null, stream);
+  int rc = run_forward(h, X, B, labels, label_bytes, W, lambda, logits_out_or_null, true, stream);
   if (rc != ASM_OK) return rc;
   if (!stats_out) return fail(h, ASM_ERR_INVALID_ARG, "stats_out is NULL%s", "");
   CU_TRY(h, cudaMemcpyAsync(stats_out, h->st.stats_local, (size_t)3 * B * sizeof(float),
@@ -348,10 +363,10 @@ int asm_forward_backward(asm_head* h, const float* X, int32_t B, const void* lab
   if (h && h->cfg.C_local != h->cfg.C_total)
     return fail(h, ASM_ERR_INVALID_ARG,
                 "asm_forward_backward needs a shard that owns every class; use the partial calls%s", "");
-  int rc = run_forward(h, X, B, labels, label_bytes, W, lambda, logits_out_or_null, stream);
+  int rc = run_forward(h, X, B, labels, label_bytes, W, lambda, logits_out_or_null, false, stream);
   if (rc != ASM_OK) return rc;
   if (!loss_out || !dX || !dW) return fail(h, ASM_ERR_INVALID_ARG, "null output pointer%s", "");
-  return run_backward(h, h->st.stats_local, 1, loss_out, dX, dW, true, stream);
+  return run_backward(h, nullptr, 1, loss_out, dX, dW, true, stream);
 }
 
 int asm_forward(asm_head* h, const float* X, int32_t B, const void* labels, int32_t label_bytes,
@@ -360,10 +375,10 @@ int asm_forward(asm_head* h, const float* X, int32_t B, const void* labels, int3
   cudaStream_t stream = (cudaStream_t)cuda_stream;
   if (h && h->cfg.C_local != h->cfg.C_total)
     return fail(h, ASM_ERR_INVALID_ARG, "asm_forward needs a shard that owns every class%s", "");
-  int rc = run_forward(h, X, B, labels, label_bytes, W, lambda, logits_out_or_null, stream);
+  int rc = run_forward(h, X, B, labels, label_bytes, W, lambda, logits_out_or_null, false, stream);
   if (rc != ASM_OK) return rc;
   if (!loss_out) return fail(h, ASM_ERR_INVALID_ARG, "loss_out is NULL%s", "");
-  return run_backward(h, h->st.stats_local, 1, loss_out, nullptr, nullptr, false, stream);
+  return run_backward(h, nullptr, 1, loss_out, nullptr, nullptr, false, stream);
 }
 
 int asm_set_profiling(asm_head* h, int enable) {

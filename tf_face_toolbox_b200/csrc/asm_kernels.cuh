@@ -36,6 +36,8 @@ struct Step {
   float* negoff;             // [B]   -(lse_i * log2 e) + log2(1/B): exp2 offset of the backward
   float* gtarget;            // [B]   G'_{i,y_i}
   float* rcoef;              // [B]   r_i  (0 if not owned)
+  float* rowloss;            // [B]   lse_i - f_{i,y}
+  unsigned int* counter;     // [1]   last-block-done ticket of the combine kernel
   float* q_part;             // [MT, Cp] column sums  sum_i G'_ij s_ij per 128-row group
   int MT;
   void* G;                   // [B, Cp]  G'' = G' * inv_c   (fp32 or bf16 by mode)
@@ -51,6 +53,8 @@ void launch_prep(const Step& s, const void* labels, int label_bytes, cudaStream_
 void launch_combine_local(const Step& s, cudaStream_t st);
 // combine [n_shards,3,B] stats into lse / loss / target coefficients
 void launch_combine_global(const Step& s, const float* stats_all, int n_shards, cudaStream_t st);
+// single shard: both of the above in one launch (partials -> stats_local, lse, loss, ...)
+void launch_combine_fused(const Step& s, cudaStream_t st);
 // dX = sum_z dx_part[z] + r_i x_i
 void launch_dx_finish(const Step& s, cudaStream_t st);
 
@@ -64,7 +68,7 @@ int simt_dx_splits(int B, int D, int Cp);
 
 // bf16 (tcgen05 / TMEM / TMA) contractions with fused epilogues
 struct UmmaMaps {            // TMA descriptors over the bf16 workspace operands
-  CUtensorMap xb_k, xb_k256, xb_mn, wb_mn, wb_k, g_k, g_mn;
+  CUtensorMap xb_k, xb_k256, xb_mn, wb_mn, wb_k, g_k, g_mn, g_st;
 };
 struct UmmaTuning {          // MN-major shared-memory descriptor parameters (bytes)
   uint32_t mn_lbo, mn_sbo, mn_kstep;
@@ -78,7 +82,8 @@ struct UmmaArgs {
 };
 cudaError_t umma_configure();
 bool umma_build_maps(UmmaMaps* m, const Step& s);
-int umma_forward_tiles(int Cp);
+int umma_forward_tiles(int B, int Cp, int num_sms);
+int umma_forward_grid(int B, int Cp, int num_sms);
 int umma_q_parts(int B);
 int umma_dx_splits(int B, int D, int Cp, int num_sms);
 void launch_umma_forward(const Step& s, const UmmaMaps& m, const UmmaTuning& tu, int num_sms,

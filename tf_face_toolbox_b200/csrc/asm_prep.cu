@@ -144,56 +144,98 @@ void launch_combine_local(const Step& s, cudaStream_t st) {
 }
 
 // ---------------------------------------------------------------------------------------
-// combine_global: one block.  Per row: M = max_g m_g, Z = sum_g z_g e^{m_g - M},
-// lse = M + log Z, loss_i = lse - f_y; then the target-column gradient coefficients
+// combine: one warp per batch row.
+//   FUSED (single shard): reduce the row's (max, sum-exp) partials, publish stats_local and
+//     continue straight to the global quantities.
+//   otherwise: reduce the [n_shards, 3, B] statistics gathered from all class shards.
+// Per row: M = max_g m_g, Z = sum_g z_g e^{m_g - M}, lse = M + log Z, loss_i = lse - f_y, the
+// exp2 offset of the backward, and the target-column gradient coefficients
 //   g_y = (e^{f_y - lse} - 1)/B,  G'_y = g_y (lambda + psi')/(1 + lambda),
 //   r   = g_y (psi - t psi') / ((1 + lambda) n)            
-// and the deterministic tree-reduced mean loss.
+// The mean loss is summed in a fixed order by the last block to finish (deterministic).
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) combine_global_kernel(Step s, const float* stats_all,
-                                                              int n_shards) {
-  __shared__ float red[1024];
-  float acc = 0.f;
-  for (int row = threadIdx.x; row < s.B; row += 1024) {
-    float M = -INFINITY;
-    for (int g = 0; g < n_shards; ++g) M = fmaxf(M, stats_all[(size_t)g * 3 * s.B + row]);
-    float Z = 0.f, fy = 0.f;
-    for (int g = 0; g < n_shards; ++g) {
-      const float* sg = stats_all + (size_t)g * 3 * s.B;
-      const float mg = sg[row];
-      if (mg > -INFINITY) Z += sg[s.B + row] * expf(mg - M);
-      fy += sg[2 * s.B + row];
+template <bool FUSED>
+__global__ void __launch_bounds__(256) combine_kernel(Step s, const float* stats_all, int n_shards) {
+  __shared__ float red[256];
+  __shared__ bool is_last;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row < s.B) {
+    float m = -INFINITY, z = 0.f, fy = 0.f;
+    if (FUSED) {
+      const float2* p = s.part + (size_t)row * s.NT;
+      for (int t = lane; t < s.NT; t += 32) {
+        const float2 v = p[t];
+        ms_combine(m, z, v.x, v.y);
+      }
+    } else {
+      for (int g = lane; g < n_shards; g += 32) {
+        const float* sg = stats_all + (size_t)g * 3 * s.B;
+        ms_combine(m, z, sg[row], sg[s.B + row]);
+        fy += sg[2 * s.B + row];
+      }
     }
-    const float lse = M + logf(Z);
-    s.lse[row] = lse;
-    s.negoff[row] = -lse * 1.4426950408889634f + log2f(s.invB);
-    acc += lse - fy;
-    float gt = 0.f, r = 0.f;
-    if (s.ylocal[row] >= 0) {
-      const float sy = s.tgt_s[row], n = s.n[row], inv_n = s.inv_n[row];
-      float psi, dpsi;
-      const float t = fminf(1.f, fmaxf(-1.f, sy * inv_n));
-      psi_eval(t, s.m, psi, dpsi);
-      const float gy = (expf(s.tgt_f[row] - lse) - 1.0f) * s.invB;
-      const float il = 1.0f / (1.0f + s.lambda);
-      gt = gy * (s.lambda + dpsi) * il;
-      r = gy * (psi - t * dpsi) * il * inv_n;
-      (void)n;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float m2 = __shfl_xor_sync(0xffffffffu, m, o);
+      const float z2 = __shfl_xor_sync(0xffffffffu, z, o);
+      ms_combine(m, z, m2, z2);
+      fy += __shfl_xor_sync(0xffffffffu, fy, o);
     }
-    s.gtarget[row] = gt;
-    s.rcoef[row] = r;
+    if (lane == 0) {
+      const bool owned = s.ylocal[row] >= 0;
+      if (FUSED) {
+        fy = owned ? s.tgt_f[row] : 0.f;
+        s.stats_local[row] = m;
+        s.stats_local[s.B + row] = z;
+        s.stats_local[2 * s.B + row] = fy;
+      }
+      const float lse = m + logf(z);
+      s.lse[row] = lse;
+      s.negoff[row] = -lse * 1.4426950408889634f + log2f(s.invB);
+      s.rowloss[row] = lse - fy;
+      float gt = 0.f, r = 0.f;
+      if (owned) {
+        const float inv_n = s.inv_n[row];
+        float psi, dpsi;
+        const float t = fminf(1.f, fmaxf(-1.f, s.tgt_s[row] * inv_n));
+        psi_eval(t, s.m, psi, dpsi);
+        const float gy = (expf(s.tgt_f[row] - lse) - 1.0f) * s.invB;
+        const float il = 1.0f / (1.0f + s.lambda);
+        gt = gy * (s.lambda + dpsi) * il;
+        r = gy * (psi - t * dpsi) * il * inv_n;
+      }
+      s.gtarget[row] = gt;
+      s.rcoef[row] = r;
+    }
   }
+  // last block done: fixed-order sum of the per-row losses
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = (atomicAdd(s.counter, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < s.B; i += 256) acc += __ldcg(s.rowloss + i);
   red[threadIdx.x] = acc;
   __syncthreads();
-  for (int o = 512; o > 0; o >>= 1) {
+  for (int o = 128; o > 0; o >>= 1) {
     if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
     __syncthreads();
   }
-  if (threadIdx.x == 0 && s.loss) *s.loss = red[0] * s.invB;
+  if (threadIdx.x == 0) {
+    if (s.loss) *s.loss = red[0] * s.invB;
+    *s.counter = 0u;
+  }
 }
 
 void launch_combine_global(const Step& s, const float* stats_all, int n_shards, cudaStream_t st) {
-  combine_global_kernel<<<1, 1024, 0, st>>>(s, stats_all, n_shards);
+  combine_kernel<false><<<(s.B + 7) / 8, 256, 0, st>>>(s, stats_all, n_shards);
+}
+
+void launch_combine_fused(const Step& s, cudaStream_t st) {
+  combine_kernel<true><<<(s.B + 7) / 8, 256, 0, st>>>(s, nullptr, 1);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -209,8 +251,19 @@ __global__ void __launch_bounds__(256) dx_finish_kernel(Step s) {
     const float4 x = __ldg(reinterpret_cast<const float4*>(s.X) + i);
     float4 a = make_float4(r * x.x, r * x.y, r * x.z, r * x.w);
     const float4* p = reinterpret_cast<const float4*>(s.dx_part) + i;
-    for (int z = 0; z < s.KS; ++z) {
-      const float4 v = p[(size_t)z * stride4];
+    int z = 0;
+    for (; z + 4 <= s.KS; z += 4) {                 // four independent loads in flight
+      const float4 v0 = __ldcg(p + (size_t)(z + 0) * stride4);
+      const float4 v1 = __ldcg(p + (size_t)(z + 1) * stride4);
+      const float4 v2 = __ldcg(p + (size_t)(z + 2) * stride4);
+      const float4 v3 = __ldcg(p + (size_t)(z + 3) * stride4);
+      a.x += v0.x; a.y += v0.y; a.z += v0.z; a.w += v0.w;
+      a.x += v1.x; a.y += v1.y; a.z += v1.z; a.w += v1.w;
+      a.x += v2.x; a.y += v2.y; a.z += v2.z; a.w += v2.w;
+      a.x += v3.x; a.y += v3.y; a.z += v3.z; a.w += v3.w;
+    }
+    for (; z < s.KS; ++z) {
+      const float4 v = __ldcg(p + (size_t)z * stride4);
       a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
     }
     reinterpret_cast<float4*>(s.dX)[i] = a;

@@ -36,7 +36,9 @@ constexpr int NUM_THREADS = 384;
 constexpr int EPI_THREADS = 256;
 constexpr int AUX_BARS = 256;                  // barriers + tmem ptr
 constexpr int AUX_VEC = 3 * 2 * BN * 4;        // per-tile vectors: 3 arrays x 2 stages x 256
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + AUX_BARS + AUX_VEC + 1024;
+constexpr int STG_HALF = 32 * 128 * 2;         // G'' staging per column half: 32 rows x 128 classes
+constexpr int AUX_STG = 2 * STG_HALF;          // 16 KB
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + AUX_BARS + AUX_VEC + AUX_STG + 1024;
 constexpr float LOG2E = 1.4426950408889634f;
 
 enum { U_FWD = 0, U_BWDG = 1, U_DW = 2, U_DX = 3 };
@@ -74,7 +76,7 @@ __device__ __noinline__ float fwd_target(float* tgt_s, float* tgt_f, const float
 template <int KIND>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-            Step s, UmmaArgs g) {
+            const __grid_constant__ CUtensorMap mapC, Step s, UmmaArgs g) {
   constexpr bool A_MN = (KIND == U_BWDG || KIND == U_DW);
   constexpr bool B_MN = (KIND == U_FWD || KIND == U_DW);
   constexpr bool N_FAST = (KIND == U_BWDG || KIND == U_DW);   // tile order: n index fastest
@@ -90,12 +92,14 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
   float* vec0 = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + AUX_BARS);  // [2][BN]
   float* vec1 = vec0 + 2 * BN;
   float* vec2 = vec1 + 2 * BN;
+  uint8_t* stg = smem + STAGES * STAGE_BYTES + AUX_BARS + AUX_VEC;                 // [2][STG_HALF]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0 && ptx::elect_one()) {
     ptx::prefetch_tmap(&mapA);
     ptx::prefetch_tmap(&mapB);
+    if (KIND == U_BWDG) ptx::prefetch_tmap(&mapC);
   }
   if (warp == 1 && ptx::elect_one()) {
     for (int i = 0; i < STAGES; ++i) {
@@ -205,6 +209,10 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
     // per-tile vectors are fetched one tile ahead into registers (pre0..2) and published to
     // shared memory at the start of their tile, so no global-load latency is exposed
     float pre0 = 0.f, pre1 = 0.f, pre2 = 0.f;
+    // FWD: the grid is a multiple of the number of row tiles, so a CTA always works on the
+    // same 128 batch rows and keeps ONE running (max, sum-exp) per thread over all its tiles
+    float run_m = -INFINITY, run_z = 0.f;
+    int fwd_row = -1;
     auto prefetch_tile = [&](int pu) {
       if (pu >= total) return;
       int pz, pm, pn;
@@ -284,7 +292,7 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
         named_bar_sync(1, EPI_THREADS);
         ptx::mbar_wait(&tfull[a], aph);
         ptx::tc_fence_after();
-        float run_m = -INFINITY, run_z = 0.f;
+        fwd_row = rv ? row : -1;
         auto process = [&](const uint32_t (&r)[32], int c) {
           const int cb = col0 + c * 32;              // column offset inside the tile
           const int jb = n0 + cb;
@@ -341,7 +349,6 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
           }
         };
         ASM_EPILOGUE_CHUNKS(process)
-        if (rv) s.part[(size_t)row * s.NT + n_idx * 2 + half] = make_float2(run_m, run_z);
       } else if (KIND == U_BWDG) {
         // ---- thread = class j (row m), columns = batch rows i.  Stage the per-row terms.
         v0[et] = pre0;
@@ -351,7 +358,11 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
         const int j = m0 + lane_row;                          // class (< Cp always)
         const float ic = s.inv_c[j];
         const float icl = ic * LOG2E;
-        __nv_bfloat16* Gw = reinterpret_cast<__nv_bfloat16*>(s.G) + j;
+        // G'' leaves through shared memory: the four warps of a column half stage a
+        // [32 rows x 128 classes] bf16 block and one thread issues a TMA store (rows >= B are
+        // clipped by the hardware), so the hot loop has no global address arithmetic at all.
+        unsigned short* stgh = reinterpret_cast<unsigned short*>(stg + half * STG_HALF) + lane_row;
+        const bool leader = (threadIdx.x == 128 + half * 128);
         named_bar_sync(1, EPI_THREADS);
         ptx::mbar_wait(&tfull[a], aph);
         ptx::tc_fence_after();
@@ -359,8 +370,6 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
         auto process = [&](const uint32_t (&r)[32], int c) {
           const int cb = col0 + c * 32;
           const int ib = n0 + cb;                             // first batch row of the chunk
-          const int nvalid = s.B - ib;                        // rows of this chunk inside the batch
-          __nv_bfloat16* gdst = Gw + (size_t)ib * s.Cp;
           float gq[32];
 #pragma unroll
           for (int b4 = 0; b4 < 8; ++b4) {
@@ -378,10 +387,16 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
               gq[b] = gp * ic;
             }
           }
+          if (leader) ptx::bulk_wait_read0();                 // previous store has drained the buffer
+          named_bar_sync(2 + half, 128);
 #pragma unroll
-          for (int b = 0; b < 32; ++b) {
-            if (b < nvalid) st_bf16(gdst, gq[b]);
-            gdst += s.Cp;
+          for (int b = 0; b < 32; ++b)
+            stgh[b * 128] = __bfloat16_as_ushort(__float2bfloat16_rn(gq[b]));
+          ptx::fence_proxy_async();                           // generic writes -> async proxy
+          named_bar_sync(2 + half, 128);
+          if (leader) {
+            ptx::tma_store_2d(&mapC, stg + half * STG_HALF, m0, ib);
+            ptx::bulk_commit();
           }
         };
         ASM_EPILOGUE_CHUNKS(process)
@@ -448,8 +463,11 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
       }
 #undef ASM_EPILOGUE_CHUNKS
     }
+    if (KIND == U_FWD && fwd_row >= 0)
+      s.part[(size_t)fwd_row * s.NT + (blockIdx.x / g.mt) * 2 + half] = make_float2(run_m, run_z);
   }
 
+  if (KIND == U_BWDG && (threadIdx.x == 128 || threadIdx.x == 256)) ptx::bulk_wait0();
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 2) ptx::tmem_dealloc(tmem_base, 512);
@@ -478,7 +496,7 @@ EncodeTiledFn get_encode_fn() {
 
 // bf16 row-major [outer, inner] tensor with `pitch` elements per row; box = {box_inner, box_outer}
 bool encode_map(CUtensorMap* m, const void* base, uint64_t inner, uint64_t outer, uint64_t pitch,
-                uint32_t box_inner, uint32_t box_outer) {
+                uint32_t box_inner, uint32_t box_outer, bool swizzle128 = true) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return false;
   cuuint64_t dims[2] = {inner, outer};
@@ -486,12 +504,24 @@ bool encode_map(CUtensorMap* m, const void* base, uint64_t inner, uint64_t outer
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
   return fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box,
-            estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+            estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 }  // namespace
 
-int umma_forward_tiles(int Cp) { return 2 * ((Cp + BN - 1) / BN); }   // 128-class partials
+// FWD grid: a multiple of the number of 128-row tiles so each CTA keeps one set of rows
+int umma_forward_grid(int B, int Cp, int num_sms) {
+  const int mt = (B + BM - 1) / BM;
+  const int total = mt * (Cp / BN);
+  const int g = (num_sms / mt) * mt;
+  return g < total ? g : total;
+}
+// (max, sum-exp) partials per row written by FWD: one per column half per CTA of that row tile
+int umma_forward_tiles(int B, int Cp, int num_sms) {
+  const int mt = (B + BM - 1) / BM;
+  return 2 * (umma_forward_grid(B, Cp, num_sms) / mt);
+}
 int umma_q_parts(int B) { return 2 * ((B + BN - 1) / BN); }            // 128-row partials
 
 int umma_dx_splits(int B, int D, int Cp, int num_sms) {
@@ -516,6 +546,7 @@ bool umma_build_maps(UmmaMaps* m, const Step& s) {
   // G'' [B, Cp]
   ok &= encode_map(&m->g_k, s.G, s.Cp, s.B, s.Cp, 64, 128);     // A of DX   (K-major, M = batch)
   ok &= encode_map(&m->g_mn, s.G, s.Cp, s.B, s.Cp, 64, 64);     // A of DW   (MN-major, M = class)
+  ok &= encode_map(&m->g_st, s.G, s.Cp, s.B, s.Cp, 128, 32, false);  // BWDG store (no swizzle)
   return ok;
 }
 
@@ -547,8 +578,7 @@ void launch_umma_forward(const Step& s, const UmmaMaps& m, const UmmaTuning& tu,
   g.nt = s.Cp / BN;
   g.kb_total = (s.D + BK - 1) / BK;
   g.kb_per = g.kb_total;
-  const int total = g.mt * g.nt;
-  umma_kernel<U_FWD><<<min(total, num_sms), NUM_THREADS, SMEM_BYTES, st>>>(m.xb_k, m.wb_mn, s, g);
+  umma_kernel<U_FWD><<<umma_forward_grid(s.B, s.Cp, num_sms), NUM_THREADS, SMEM_BYTES, st>>>(m.xb_k, m.wb_mn, m.wb_mn, s, g);
 }
 
 void launch_umma_bwdg(const Step& s, const UmmaMaps& m, const UmmaTuning& tu, int num_sms,
@@ -558,7 +588,7 @@ void launch_umma_bwdg(const Step& s, const UmmaMaps& m, const UmmaTuning& tu, in
   g.nt = (s.B + BN - 1) / BN;
   g.kb_total = (s.D + BK - 1) / BK;
   g.kb_per = g.kb_total;
-  umma_kernel<U_BWDG><<<min(g.mt * g.nt, num_sms), NUM_THREADS, SMEM_BYTES, st>>>(m.wb_mn, m.xb_k256, s, g);
+  umma_kernel<U_BWDG><<<min(g.mt * g.nt, num_sms), NUM_THREADS, SMEM_BYTES, st>>>(m.wb_mn, m.xb_k256, m.g_st, s, g);
 }
 
 void launch_umma_dw(const Step& s, const UmmaMaps& m, const UmmaTuning& tu, int num_sms,
@@ -568,7 +598,7 @@ void launch_umma_dw(const Step& s, const UmmaMaps& m, const UmmaTuning& tu, int 
   g.nt = (s.D + BN - 1) / BN;
   g.kb_total = (s.B + BK - 1) / BK;
   g.kb_per = g.kb_total;
-  umma_kernel<U_DW><<<min(g.mt * g.nt, num_sms), NUM_THREADS, SMEM_BYTES, st>>>(m.g_mn, m.xb_mn, s, g);
+  umma_kernel<U_DW><<<min(g.mt * g.nt, num_sms), NUM_THREADS, SMEM_BYTES, st>>>(m.g_mn, m.xb_mn, m.xb_mn, s, g);
 }
 
 void launch_umma_dx(const Step& s, const UmmaMaps& m, const UmmaTuning& tu, int num_sms,
@@ -579,7 +609,7 @@ void launch_umma_dx(const Step& s, const UmmaMaps& m, const UmmaTuning& tu, int 
   g.kb_total = (s.Cp + BK - 1) / BK;
   g.ks = s.KS;
   g.kb_per = (g.kb_total + g.ks - 1) / g.ks;
-  umma_kernel<U_DX><<<min(g.mt * g.nt * g.ks, num_sms), NUM_THREADS, SMEM_BYTES, st>>>(m.g_k, m.wb_k, s, g);
+  umma_kernel<U_DX><<<min(g.mt * g.nt * g.ks, num_sms), NUM_THREADS, SMEM_BYTES, st>>>(m.g_k, m.wb_k, m.wb_k, s, g);
 }
 
 }  // namespace asmh
