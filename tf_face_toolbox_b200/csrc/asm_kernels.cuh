@@ -68,7 +68,7 @@ int simt_dx_splits(int B, int D, int Cp);
 
 // bf16 (tcgen05 / TMEM / TMA) contractions with fused epilogues
 struct UmmaMaps {            // TMA descriptors over the bf16 workspace operands
-  CUtensorMap xb_k, xb_k256, xb_mn, wb_mn, wb_k, g_k, g_mn, g_st;
+  CUtensorMap xb_k, xb_k256, xb_mn, wb_mn, wb_k, g_k, g_mn, g_st, wb_box;
 };
 struct UmmaTuning {          // MN-major shared-memory descriptor parameters (bytes)
   uint32_t mn_lbo, mn_sbo, mn_kstep;

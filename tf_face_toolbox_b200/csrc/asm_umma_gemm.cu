@@ -38,7 +38,12 @@ constexpr int AUX_BARS = 256;                  // barriers + tmem ptr
 constexpr int AUX_VEC = 3 * 2 * BN * 4;        // per-tile vectors: 3 arrays x 2 stages x 256
 constexpr int STG_HALF = 32 * 128 * 2;         // G'' staging per column half: 32 rows x 128 classes
 constexpr int AUX_STG = 2 * STG_HALF;          // 16 KB
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + AUX_BARS + AUX_VEC + AUX_STG + 1024;
+constexpr int WB_BUF = 32 * 128 * 2;           // DW: one [32 d x 128 classes] bf16 weight chunk
+constexpr int AUX_WB = 2 * 2 * WB_BUF;         // 2 column halves x 2 buffers = 32 KB
+// the region after the barriers holds vec + stg (FWD / BWDG) or the weight-chunk ring (DW)
+constexpr int AUX_REGION = (AUX_VEC + AUX_STG) > AUX_WB ? (AUX_VEC + AUX_STG) : AUX_WB;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + AUX_BARS + AUX_REGION + 1024;
+static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB shared memory of an sm_100 CTA");
 constexpr float LOG2E = 1.4426950408889634f;
 
 enum { U_FWD = 0, U_BWDG = 1, U_DW = 2, U_DX = 3 };
@@ -88,18 +93,21 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
   uint64_t* empty = full + STAGES;
   uint64_t* tfull = empty + STAGES;
   uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2 + 8);
   float* vec0 = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + AUX_BARS);  // [2][BN]
   float* vec1 = vec0 + 2 * BN;
   float* vec2 = vec1 + 2 * BN;
   uint8_t* stg = smem + STAGES * STAGE_BYTES + AUX_BARS + AUX_VEC;                 // [2][STG_HALF]
+  uint8_t* wbuf = smem + STAGES * STAGE_BYTES + AUX_BARS;                          // DW: [2][2][WB_BUF]
+  uint64_t* wfull = tempty + 4;                                                    // DW: [half][buf]
+  uint64_t* wempty = wfull + 4;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0 && ptx::elect_one()) {
     ptx::prefetch_tmap(&mapA);
     ptx::prefetch_tmap(&mapB);
-    if (KIND == U_BWDG) ptx::prefetch_tmap(&mapC);
+    if (KIND == U_BWDG || KIND == U_DW) ptx::prefetch_tmap(&mapC);
   }
   if (warp == 1 && ptx::elect_one()) {
     for (int i = 0; i < STAGES; ++i) {
@@ -109,6 +117,10 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&tfull[a], 1);
       ptx::mbar_init(&tempty[a], EPI_THREADS);
+    }
+    for (int i = 0; i < 4; ++i) {
+      ptx::mbar_init(&wfull[i], 1);
+      ptx::mbar_init(&wempty[i], 128);
     }
     ptx::fence_barrier_init();
   }
@@ -198,6 +210,28 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
         ptx::umma_commit(&tfull[a]);        // accumulator ready for the epilogue
       }
     }
+  } else if (warp == 3) {
+    // ------------------------------------------------------------ DW: weight-chunk producer
+    // Streams the bf16 weight block of each tile ([256 d x 128 classes], needed by the
+    // normalisation-Jacobian correction in the epilogue) through a 2-deep ring per column
+    // half, so the epilogue never waits on a global load.
+    if (KIND == U_DW && !(g.debug_flags & 1) && ptx::elect_one()) {
+      uint32_t cc = 0;
+      for (int u = blockIdx.x; u < total; u += gridDim.x) {
+        int z, m_idx, n_idx;
+        decode(u, z, m_idx, n_idx);
+        for (int c = 0; c < 4; ++c, ++cc) {
+          const uint32_t buf = cc & 1, ph = (cc >> 1) & 1;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            ptx::mbar_wait(&wempty[h * 2 + buf], ph ^ 1);
+            ptx::mbar_expect_tx(&wfull[h * 2 + buf], WB_BUF);
+            ptx::tma_load_2d(wbuf + (h * 2 + buf) * WB_BUF, &mapC, &wfull[h * 2 + buf],
+                             m_idx * BM, n_idx * BN + h * 128 + c * 32);
+          }
+        }
+      }
+    }
   } else if (warp >= 4) {
     // ------------------------------------------------------------ epilogue (256 threads)
     const int q4 = warp & 3;                  // TMEM lane quarter this warp may access
@@ -208,7 +242,7 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
     uint32_t lt = 0;
     // per-tile vectors are fetched one tile ahead into registers (pre0..2) and published to
     // shared memory at the start of their tile, so no global-load latency is exposed
-    float pre0 = 0.f, pre1 = 0.f, pre2 = 0.f;
+    float pre0 = 0.f, pre1 = 0.f, pre2 = 0.f, pre3 = 0.f;
     // FWD: the grid is a multiple of the number of row tiles, so a CTA always works on the
     // same 128 batch rows and keeps ONE running (max, sum-exp) per thread over all its tiles
     float run_m = -INFINITY, run_z = 0.f;
@@ -226,18 +260,14 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
         pre2 = iv ? s.gtarget[i] : 0.f;
       }
       if (KIND == U_DW) {
+        // raw loads only (no arithmetic here, so nothing waits on them until the next tile)
         const int pj = pm * BM + lane_row;
-        float c = 0.f;
-        for (int t = 0; t < s.MT; ++t) c += s.q_part[(size_t)t * s.Cp + pj];
-        const float pic = s.inv_c[pj];
-        pre0 = -c * pic * pic;
-        // pull the bf16 weight block of that tile [256 d x 128 classes] into L2
-        const int d = pn * BN + et;
-        if (d < s.D) {
-          const char* pw = reinterpret_cast<const char*>(s.Wb + (size_t)d * s.Cp + pm * BM);
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(pw));
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(pw + 128));
-        }
+        const float* qp = s.q_part + pj;
+        pre0 = qp[0];
+        pre1 = s.MT > 1 ? qp[(size_t)s.Cp] : 0.f;
+        pre2 = s.inv_c[pj];
+        pre3 = 0.f;
+        for (int t = 2; t < s.MT; ++t) pre3 += qp[(size_t)t * s.Cp];
       }
     };
     prefetch_tile(blockIdx.x);
@@ -403,38 +433,29 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
         s.q_part[(size_t)(n_idx * 2 + half) * s.Cp + j] = (q0 + q1) * ic;
       } else if (KIND == U_DW) {
         // ---- thread = class j, columns = d.  dW[d][j] = acc - Wb[d][j] * q_j / c_j^2
-        // coef = -q_j / c_j^2 was computed one tile ahead (and the weight block pulled into
-        // L2); the bf16 weights of chunk c+1 are fetched while chunk c is written.
+        // The q_j partials and 1/c_j were fetched one tile ahead; the bf16 weight chunks
+        // arrive through the TMA ring filled by warp 3.
         const int j = m0 + lane_row;
         const bool jv = j < s.C;
-        const float coef = pre0;
+        const float coef = -((pre0 + pre1) + pre3) * pre2 * pre2;
         prefetch_tile(u + gridDim.x);
         const int d_first = n0 + col0;
-        const unsigned short* wsrc =
-            reinterpret_cast<const unsigned short*>(s.Wb) + (size_t)d_first * s.Cp + j;
-        unsigned short wq[32];
-        auto fetch_w = [&](int c) {
-          if (d_first + c * 32 < s.D) {                       // D % 32 == 0 in bf16 mode
-            const unsigned short* p = wsrc + (size_t)(c * 32) * s.Cp;
-#pragma unroll
-            for (int b = 0; b < 32; ++b) {
-              wq[b] = __ldg(p);
-              p += s.Cp;
-            }
-          }
-        };
-        fetch_w(0);
         ptx::mbar_wait(&tfull[a], aph);
         ptx::tc_fence_after();
         auto process = [&](const uint32_t (&r)[32], int c) {
-          const int db = d_first + c * 32;                    // first d of the chunk
+          const uint32_t cc = lt * 4 + c;                     // chunk counter of this half
+          const uint32_t buf = cc & 1, ph = (cc >> 1) & 1;
+          const unsigned short* wsm =
+              reinterpret_cast<const unsigned short*>(wbuf + (half * 2 + buf) * WB_BUF) + lane_row;
+          ptx::mbar_wait(&wfull[half * 2 + buf], ph);
           float o[32];
 #pragma unroll
           for (int b = 0; b < 32; ++b)
-            o[b] = fmaf(__uint_as_float(static_cast<uint32_t>(wq[b]) << 16), coef,
+            o[b] = fmaf(__uint_as_float(static_cast<uint32_t>(wsm[b * 128]) << 16), coef,
                         __uint_as_float(r[b]));
-          if (c < 3) fetch_w(c + 1);
-          if (jv && db < s.D) {
+          ptx::mbar_arrive(&wempty[half * 2 + buf]);         // chunk consumed (values in o[])
+          const int db = d_first + c * 32;                    // first d of the chunk
+          if (jv && db < s.D && !(g.debug_flags & 2)) {       // D % 32 == 0 in bf16 mode
             float* dst = s.dW + (size_t)db * s.C + j;
 #pragma unroll
             for (int b = 0; b < 32; ++b) {
@@ -547,6 +568,7 @@ bool umma_build_maps(UmmaMaps* m, const Step& s) {
   ok &= encode_map(&m->g_k, s.G, s.Cp, s.B, s.Cp, 64, 128);     // A of DX   (K-major, M = batch)
   ok &= encode_map(&m->g_mn, s.G, s.Cp, s.B, s.Cp, 64, 64);     // A of DW   (MN-major, M = class)
   ok &= encode_map(&m->g_st, s.G, s.Cp, s.B, s.Cp, 128, 32, false);  // BWDG store (no swizzle)
+  ok &= encode_map(&m->wb_box, s.Wb, s.Cp, s.D, s.Cp, 128, 32, false);  // DW weight chunks
   return ok;
 }
 
@@ -598,7 +620,7 @@ void launch_umma_dw(const Step& s, const UmmaMaps& m, const UmmaTuning& tu, int 
   g.nt = (s.D + BN - 1) / BN;
   g.kb_total = (s.B + BK - 1) / BK;
   g.kb_per = g.kb_total;
-  umma_kernel<U_DW><<<min(g.mt * g.nt, num_sms), NUM_THREADS, SMEM_BYTES, st>>>(m.g_mn, m.xb_mn, m.xb_mn, s, g);
+  umma_kernel<U_DW><<<min(g.mt * g.nt, num_sms), NUM_THREADS, SMEM_BYTES, st>>>(m.g_mn, m.xb_mn, m.wb_box, s, g);
 }
 
 void launch_umma_dx(const Step& s, const UmmaMaps& m, const UmmaTuning& tu, int num_sms,
