@@ -242,7 +242,7 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
     uint32_t lt = 0;
     // per-tile vectors are fetched one tile ahead into registers (pre0..2) and published to
     // shared memory at the start of their tile, so no global-load latency is exposed
-    float pre0 = 0.f, pre1 = 0.f, pre2 = 0.f, pre3 = 0.f;
+    float pre0 = 0.f, pre1 = 0.f, pre2 = 0.f, pre3 = 0.f, pre4 = 0.f, pre5 = 0.f;
     // FWD: the grid is a multiple of the number of row tiles, so a CTA always works on the
     // same 128 batch rows and keeps ONE running (max, sum-exp) per thread over all its tiles
     float run_m = -INFINITY, run_z = 0.f;
@@ -266,8 +266,10 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
         pre0 = qp[0];
         pre1 = s.MT > 1 ? qp[(size_t)s.Cp] : 0.f;
         pre2 = s.inv_c[pj];
-        pre3 = 0.f;
-        for (int t = 2; t < s.MT; ++t) pre3 += qp[(size_t)t * s.Cp];
+        pre3 = s.MT > 2 ? qp[(size_t)2 * s.Cp] : 0.f;
+        pre4 = s.MT > 3 ? qp[(size_t)3 * s.Cp] : 0.f;
+        pre5 = 0.f;
+        for (int t = 4; t < s.MT; ++t) pre5 += qp[(size_t)t * s.Cp];   // batches > 512 rows
       }
     };
     prefetch_tile(blockIdx.x);
@@ -437,7 +439,7 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
         // arrive through the TMA ring filled by warp 3.
         const int j = m0 + lane_row;
         const bool jv = j < s.C;
-        const float coef = -((pre0 + pre1) + pre3) * pre2 * pre2;
+        const float coef = -(((pre0 + pre1) + (pre3 + pre4)) + pre5) * pre2 * pre2;
         prefetch_tile(u + gridDim.x);
         const int d_first = n0 + col0;
         ptx::mbar_wait(&tfull[a], aph);

@@ -96,9 +96,10 @@ class ShardedASoftmaxHead:
     def _all_gather(self, t: torch.Tensor) -> torch.Tensor:
         if self.world == 1:
             return t
-        out = torch.empty((self.world,) + tuple(t.shape), device=t.device, dtype=t.dtype)
-        dist.all_gather_into_tensor(out, t.contiguous(), group=self.group)
-        return out
+        t = t.contiguous()
+        out = torch.empty((self.world * t.shape[0],) + tuple(t.shape[1:]), device=t.device, dtype=t.dtype)
+        dist.all_gather_into_tensor(out, t, group=self.group)      # concatenated along dim 0
+        return out.view((self.world,) + tuple(t.shape))
 
     def _reduce_scatter_rows(self, full: torch.Tensor, rows_local: int) -> torch.Tensor:
         if self.world == 1:
