@@ -290,14 +290,17 @@ def run_ours(args, cfg):
     t_load1 = time.time()
     e2e_value = B / (ms_e2e * 1e-3)
 
-    # keep the GPU under the same load long enough for nvidia-smi to sample clocks
-    if rank == 0 and (t_load1 - t_load0) < 1.0:
-        t_end = time.time() + 1.2
-        while time.time() < t_end:
-            for _ in range(20):
-                step()
-            torch.cuda.synchronize()
-        t_load1 = time.time()
+    # keep the GPU under the same load long enough for nvidia-smi to sample clocks; the
+    # number of extra (untimed) steps is derived from the all-reduced step time so that every
+    # rank issues the same collectives
+    n_extra = min(20000, int(1200.0 / max(ms_step, 1e-3)))
+    done = 0
+    while done < n_extra:
+        for _ in range(min(50, n_extra - done)):
+            step()
+        done += 50
+        torch.cuda.synchronize()
+    t_load1 = time.time()
     clocks = sampler.stop(t_load0, t_load1) if rank == 0 else None
     if world > 1:
         dist.barrier()
