@@ -175,6 +175,7 @@ def run_ours(args, cfg):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")      # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     B, D, Cn, mode = cfg["B"], cfg["D"], cfg["C"], args.mode
     K, Wm = args.steps, args.warmup
@@ -252,25 +253,20 @@ def run_ours(args, cfg):
 
     # ---- (2) per-kernel durations (CUDA events on the launching stream, inside the library)
     kernels = {}
-    launches_per_step = 0
-    if world == 1:
-        h = get_handle(dev, D, Cn, Cn, 0, B, M_MARGIN, mode)
-        launches_per_step = int(h.lib.asm_last_launch_count(h.ptr))
-        h.lib.asm_set_profiling(h.ptr, 1)
-        ms_buf = (C.c_float * 16)()
-        names = C.create_string_buffer(16 * 32)
-        for _ in range(K):
-            if flush is not None:
-                flush.zero_()
-            step()
-            n = h.lib.asm_get_profile(h.ptr, 16, ms_buf, names)
-            for i in range(max(n, 0)):
-                nm = names.raw[i * 32:(i + 1) * 32].split(b"\0")[0].decode()
-                kernels.setdefault(nm, []).append(ms_buf[i])
-        h.lib.asm_set_profiling(h.ptr, 0)
-    else:
-        sh = head.compute._handle(B)
-        launches_per_step = int(sh.lib.asm_last_launch_count(sh.ptr))
+    h = get_handle(dev, D, Cn, Cn, 0, B, M_MARGIN, mode) if world == 1 else head.compute._handle(B)
+    launches_per_step = int(h.lib.asm_last_launch_count(h.ptr))
+    h.lib.asm_set_profiling(h.ptr, 1)
+    ms_buf = (C.c_float * 16)()
+    names = C.create_string_buffer(16 * 32)
+    for _ in range(K):
+        if flush is not None:
+            flush.zero_()
+        step()
+        n = h.lib.asm_get_profile(h.ptr, 16, ms_buf, names)
+        for i in range(max(n, 0)):
+            nm = names.raw[i * 32:(i + 1) * 32].split(b"\0")[0].decode()
+            kernels.setdefault(nm, []).append(ms_buf[i])
+    h.lib.asm_set_profiling(h.ptr, 0)
     kavg = {k: sum(v) / len(v) for k, v in kernels.items()}
 
     # ---- (3) end to end through the public Python API with HOST buffers

@@ -219,6 +219,9 @@ int run_backward(asm_head* h, const float* stats_all, int n_shards, float* loss_
   s.dW = dW;
   const bool tc = h->cfg.mode == ASM_MODE_BF16;
   if (stats_all) {
+    // profiling: the gap between the two halves is the host-side statistics all-gather
+    if (h->profiling && h->n_marks > 0 && h->n_marks < asm_head::kMaxMarks)
+      h->mark_name[h->n_marks++] = "stats_exchange_host";
     mark(h, "combine_global", stream);
     launch_combine_global(s, stats_all, n_shards, stream);
   } else {
