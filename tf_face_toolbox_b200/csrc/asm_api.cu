@@ -27,6 +27,11 @@ struct asm_head {
   int maps_B = -1;
   UmmaTuning tune{8192, 1024, 2048, 0};
   bool fwd_valid = false;
+  // dX branch of the backward (DX + dx_finish) runs on a second stream so that it fills the
+  // SMs the DW kernel's tail leaves idle; both only depend on G'' from the BWDG kernel
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool overlap = true;           // ASM_NO_OVERLAP=1 disables
   size_t l2_persist_bytes = 0;   // ASM_L2_PERSIST_MB: pin the bf16 weight copy in L2
   cudaStream_t l2_stream = nullptr;
   bool l2_set = false;
@@ -232,14 +237,26 @@ int run_backward(asm_head* h, const float* stats_all, int n_shards, float* loss_
     mark(h, "bwd_recompute_g", stream);
     if (tc) launch_umma_bwdg(s, h->maps, h->tune, h->num_sms, stream);
     else launch_simt_bwdg(s, stream);
+    // the per-kernel profile needs one stream; otherwise fork the dX branch
+    const bool fork = h->overlap && !h->profiling && h->side != nullptr;
+    cudaStream_t sx = stream;
+    if (fork) {
+      cudaEventRecord(h->ev_fork, stream);
+      cudaStreamWaitEvent(h->side, h->ev_fork, 0);
+      sx = h->side;
+    }
     mark(h, "dw_gemm", stream);
     if (tc) launch_umma_dw(s, h->maps, h->tune, h->num_sms, stream);
     else launch_simt_dw(s, stream);
-    mark(h, "dx_gemm", stream);
-    if (tc) launch_umma_dx(s, h->maps, h->tune, h->num_sms, stream);
-    else launch_simt_dx(s, stream);
-    mark(h, "dx_finish", stream);
-    launch_dx_finish(s, stream);
+    mark(h, "dx_gemm", sx);
+    if (tc) launch_umma_dx(s, h->maps, h->tune, h->num_sms, sx);
+    else launch_simt_dx(s, sx);
+    mark(h, "dx_finish", sx);
+    launch_dx_finish(s, sx);
+    if (fork) {
+      cudaEventRecord(h->ev_join, h->side);
+      cudaStreamWaitEvent(stream, h->ev_join, 0);
+    }
   }
   mark_end(h, stream);
   return check_launch(h, "backward launch");
@@ -287,6 +304,13 @@ int asm_create(asm_head** out, const asm_config* cfg) {
   if ((e = getenv("ASM_UMMA_MN_SBO"))) h->tune.mn_sbo = (uint32_t)atoi(e);
   if ((e = getenv("ASM_UMMA_MN_KSTEP"))) h->tune.mn_kstep = (uint32_t)atoi(e);
   if ((e = getenv("ASM_UMMA_DEBUG"))) h->tune.debug_flags = (uint32_t)atoi(e);
+  if ((e = getenv("ASM_NO_OVERLAP")) && atoi(e)) h->overlap = false;
+  if (cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+    cudaGetLastError();
+    h->side = nullptr;
+  }
   if ((e = getenv("ASM_L2_PERSIST_MB"))) h->l2_persist_bytes = (size_t)atoi(e) << 20;
   const Layout L = make_layout(*cfg, h->num_sms);
   cudaError_t ce = cudaMalloc(&h->ws, L.total);
@@ -346,6 +370,9 @@ int asm_create(asm_head** out, const asm_config* cfg) {
 int asm_destroy(asm_head* h) {
   if (!h) return ASM_ERR_INVALID_ARG;
   if (h->ws) cudaFree(h->ws);
+  if (h->side) cudaStreamDestroy(h->side);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
   if (h->ev[0])
     for (int i = 0; i <= asm_head::kMaxMarks; ++i) cudaEventDestroy(h->ev[i]);
   delete h;

@@ -68,11 +68,11 @@ int simt_dx_splits(int B, int D, int Cp);
 
 // bf16 (tcgen05 / TMEM / TMA) contractions with fused epilogues
 struct UmmaMaps {            // TMA descriptors over the bf16 workspace operands
-  CUtensorMap xb_k, xb_k256, xb_mn, wb_mn, wb_k, g_k, g_mn, g_st, wb_box;
+  CUtensorMap xb_k, xb_k256, xb_mn, wb_mn, wb_mn32, wb_k, g_k, g_mn, g_st, wb_box;
 };
 struct UmmaTuning {          // MN-major shared-memory descriptor parameters (bytes)
   uint32_t mn_lbo, mn_sbo, mn_kstep;
-  uint32_t debug_flags;      // bit0: skip epilogue math (ASM_UMMA_DEBUG, bring-up only)
+  uint32_t debug_flags;      // bit0: skip epilogue math, bit1: DW without stores, bit2: X-resident forward variant (ASM_UMMA_DEBUG, bring-up only)
 };
 struct UmmaArgs {
   int mt, nt, ks, kb_total, kb_per;

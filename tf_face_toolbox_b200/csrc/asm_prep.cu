@@ -1,12 +1,14 @@
 // HBM-bound kernels of the A-softmax head: norms (+ bf16 operand copies), stats combine,
 // dX finish.  See DESIGN.md "Kernels" for the per-kernel roofline and algorithmic bytes.
+#include <stdlib.h>
+
 #include "asm_common.cuh"
 #include "asm_kernels.cuh"
 
 namespace asmh {
 
 // ---------------------------------------------------------------------------------------
-// prep: one launch, two roles.
+// prep: one launch, two roles (block = TX column pairs x TY row groups).
 //   blocks [0, nwb): W role. Block (32 x 8) owns 64 columns; thread (tx, ty) owns the column
 //     pair 2*(blk*32+tx) and the rows ty, ty+8, ...  Loads are coalesced along C (a warp
 //     reads 256 contiguous bytes per row), the bf16 copy is written with the same mapping
@@ -15,13 +17,15 @@ namespace asmh {
 //   blocks [nwb, ...): X role. One warp per embedding row: n_i, 1/n_i, bf16 copy, and the
 //     label -> local-class-index translation with the range check.
 // ---------------------------------------------------------------------------------------
-template <bool VEC2, bool BF16>
+template <bool VEC2, bool BF16, int TX, int TY>
 __global__ void __launch_bounds__(256) prep_kernel(Step s, const void* labels, int label_bytes,
                                                    int nwb) {
-  __shared__ float red[8][64];
-  const int tx = threadIdx.x, ty = threadIdx.y;
+  static_assert(TX * TY == 256, "256 threads");
+  __shared__ float red[TY][2 * TX];
+  const int tid = threadIdx.x;
   if ((int)blockIdx.x < nwb) {
-    const int j0 = (blockIdx.x * 32 + tx) * 2;
+    const int tx = tid % TX, ty = tid / TX;
+    const int j0 = (blockIdx.x * TX + tx) * 2;
     float a0 = 0.f, a1 = 0.f;
     if (j0 < s.Cp) {
       const bool v0 = j0 < s.C, v1 = j0 + 1 < s.C;
@@ -30,11 +34,11 @@ __global__ void __launch_bounds__(256) prep_kernel(Step s, const void* labels, i
       // U rows per trip: all loads are issued before the first use so that U x 8 B per
       // thread are in flight (the bf16 stores would otherwise serialise the loads).
       constexpr int U = 16;
-      for (int d0 = ty; d0 < s.D; d0 += 8 * U) {
+      for (int d0 = ty; d0 < s.D; d0 += TY * U) {
         float x0[U], x1[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          const int d = d0 + 8 * u;
+          const int d = d0 + TY * u;
           x0[u] = 0.f; x1[u] = 0.f;
           if (d < s.D) {
             if (VEC2) {
@@ -52,7 +56,7 @@ __global__ void __launch_bounds__(256) prep_kernel(Step s, const void* labels, i
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          const int d = d0 + 8 * u;
+          const int d = d0 + TY * u;
           a0 = fmaf(x0[u], x0[u], a0);
           a1 = fmaf(x1[u], x1[u], a1);
           if (BF16 && d < s.D)
@@ -64,16 +68,16 @@ __global__ void __launch_bounds__(256) prep_kernel(Step s, const void* labels, i
     red[ty][tx * 2] = a0;
     red[ty][tx * 2 + 1] = a1;
     __syncthreads();
-    const int t = ty * 32 + tx;
-    if (t < 64) {
+    for (int t = tid; t < 2 * TX; t += 256) {
       float acc = 0.f;
 #pragma unroll
-      for (int r = 0; r < 8; ++r) acc += red[r][t];
-      const int j = blockIdx.x * 64 + t;
+      for (int r = 0; r < TY; ++r) acc += red[r][t];
+      const int j = blockIdx.x * 2 * TX + t;
       if (j < s.Cp) s.inv_c[j] = (j < s.C && acc > 0.f) ? rsqrtf(acc) : 0.f;
     }
   } else {
-    const int row = (blockIdx.x - nwb) * 8 + ty;
+    const int tx = tid & 31;
+    const int row = (blockIdx.x - nwb) * 8 + (tid >> 5);
     if (row >= s.B) return;
     const float* x = s.X + (size_t)row * s.D;
     float acc = 0.f;
@@ -98,19 +102,30 @@ __global__ void __launch_bounds__(256) prep_kernel(Step s, const void* labels, i
   }
 }
 
-void launch_prep(const Step& s, const void* labels, int label_bytes, cudaStream_t st) {
-  const int nwb = (s.Cp + 63) / 64;
+template <int TX, int TY>
+static void launch_prep_t(const Step& s, const void* labels, int label_bytes, cudaStream_t st) {
+  const int nwb = (s.Cp + 2 * TX - 1) / (2 * TX);
   const int nxb = (s.B + 7) / 8;
   const bool vec2 = (s.C % 2 == 0) && ((reinterpret_cast<uintptr_t>(s.W) & 7) == 0);
-  dim3 blk(32, 8);
   dim3 grd(nwb + nxb);
   if (s.mode == 1) {
-    if (vec2) prep_kernel<true, true><<<grd, blk, 0, st>>>(s, labels, label_bytes, nwb);
-    else prep_kernel<false, true><<<grd, blk, 0, st>>>(s, labels, label_bytes, nwb);
+    if (vec2) prep_kernel<true, true, TX, TY><<<grd, 256, 0, st>>>(s, labels, label_bytes, nwb);
+    else prep_kernel<false, true, TX, TY><<<grd, 256, 0, st>>>(s, labels, label_bytes, nwb);
   } else {
-    if (vec2) prep_kernel<true, false><<<grd, blk, 0, st>>>(s, labels, label_bytes, nwb);
-    else prep_kernel<false, false><<<grd, blk, 0, st>>>(s, labels, label_bytes, nwb);
+    if (vec2) prep_kernel<true, false, TX, TY><<<grd, 256, 0, st>>>(s, labels, label_bytes, nwb);
+    else prep_kernel<false, false, TX, TY><<<grd, 256, 0, st>>>(s, labels, label_bytes, nwb);
   }
+}
+
+void launch_prep(const Step& s, const void* labels, int label_bytes, cudaStream_t st) {
+  static int shape = -1;                       // ASM_PREP_SHAPE: 0 = 32x8, 1 = 128x2, 2 = 256x1
+  if (shape < 0) {
+    const char* e = getenv("ASM_PREP_SHAPE");
+    shape = e ? atoi(e) : 0;
+  }
+  if (shape == 1) launch_prep_t<128, 2>(s, labels, label_bytes, st);
+  else if (shape == 2) launch_prep_t<256, 1>(s, labels, label_bytes, st);
+  else launch_prep_t<32, 8>(s, labels, label_bytes, st);
 }
 
 // ---------------------------------------------------------------------------------------

@@ -42,11 +42,29 @@ constexpr int WB_BUF = 32 * 128 * 2;           // DW: one [32 d x 128 classes] b
 constexpr int AUX_WB = 2 * 2 * WB_BUF;         // 2 column halves x 2 buffers = 32 KB
 // the region after the barriers holds vec + stg (FWD / BWDG) or the weight-chunk ring (DW)
 constexpr int AUX_REGION = (AUX_VEC + AUX_STG) > AUX_WB ? (AUX_VEC + AUX_STG) : AUX_WB;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + AUX_BARS + AUX_REGION + 1024;
-static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB shared memory of an sm_100 CTA");
 constexpr float LOG2E = 1.4426950408889634f;
 
-enum { U_FWD = 0, U_BWDG = 1, U_DW = 2, U_DX = 3 };
+// U_FWDR is an experimental forward kernel with the CTA's 128-row block of Xb RESIDENT in
+// shared memory (D <= 512): only the weight tiles stream (32-deep K stages, 5 of them), which
+// cuts the L2 -> SM operand traffic by a third.  Measured SLOWER than the streaming kernel
+// (55 vs 48 us at cfg 3): the pipeline is bound by bytes in flight (80 KB vs 192 KB), not by
+// L2 bandwidth.  Kept behind ASM_UMMA_DEBUG bit 2 as the record of that experiment.
+enum { U_FWD = 0, U_BWDG = 1, U_DW = 2, U_DX = 3, U_FWDR = 4 };
+
+// pipeline geometry per kernel kind
+template <int KIND> struct Geo {
+  static constexpr bool RES = (KIND == U_FWDR);
+  static constexpr int KB = RES ? 32 : BK;                 // K elements per pipeline stage
+  static constexpr int NST = RES ? 5 : STAGES;             // pipeline depth
+  static constexpr int A_ST = RES ? 0 : BM * KB * 2;       // A bytes per stage
+  static constexpr int B_ST = BN * KB * 2;                 // B bytes per stage
+  static constexpr int ST_B = A_ST + B_ST;
+  static constexpr int RES_B = RES ? 8 * A_BYTES : 0;      // resident A block (K <= 512)
+  static constexpr int CH_B = 64 * KB * 2;                 // one 64-wide MN-major chunk
+  static constexpr int PIPE_B = RES_B + NST * ST_B;
+  static constexpr int SMEM = PIPE_B + AUX_BARS + (RES ? AUX_VEC : AUX_REGION) + 1024;
+  static_assert(SMEM <= 232448, "exceeds the 227 KB shared memory of an sm_100 CTA");
+};
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -82,25 +100,31 @@ template <int KIND>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
             const __grid_constant__ CUtensorMap mapC, Step s, UmmaArgs g) {
+  using G_ = Geo<KIND>;
+  constexpr bool IS_FWD = (KIND == U_FWD || KIND == U_FWDR);
+  constexpr bool RES = G_::RES;
+  constexpr int KB = G_::KB, NST = G_::NST, A_ST = G_::A_ST, ST_B = G_::ST_B;
+  constexpr int RES_B = G_::RES_B, CH_B = G_::CH_B, PIPE_B = G_::PIPE_B;
   constexpr bool A_MN = (KIND == U_BWDG || KIND == U_DW);
-  constexpr bool B_MN = (KIND == U_FWD || KIND == U_DW);
+  constexpr bool B_MN = (IS_FWD || KIND == U_DW);
   constexpr bool N_FAST = (KIND == U_BWDG || KIND == U_DW);   // tile order: n index fastest
   extern __shared__ uint8_t smem_raw[];
   // align to 1024 B (SWIZZLE_128B atoms) by adding an integer offset, so that the compiler
   // keeps the shared address space (ld.shared, not generic loads) for everything below
   uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
-  uint64_t* empty = full + STAGES;
-  uint64_t* tfull = empty + STAGES;
-  uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2 + 8);
-  float* vec0 = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + AUX_BARS);  // [2][BN]
+  uint8_t* pipe = smem + RES_B;                                       // stage ring
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + PIPE_B);        // [8] (NST used)
+  uint64_t* empty = full + 8;                                         // [8]
+  uint64_t* tfull = empty + 8;                                        // [2]
+  uint64_t* tempty = tfull + 2;                                       // [2]
+  uint64_t* wfull = tempty + 2;                                       // DW: [half][buf]; FWDR: [0] = X resident
+  uint64_t* wempty = wfull + 4;                                       // DW: [half][buf]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(wempty + 4);
+  float* vec0 = reinterpret_cast<float*>(smem + PIPE_B + AUX_BARS);   // [2][BN]
   float* vec1 = vec0 + 2 * BN;
   float* vec2 = vec1 + 2 * BN;
-  uint8_t* stg = smem + STAGES * STAGE_BYTES + AUX_BARS + AUX_VEC;                 // [2][STG_HALF]
-  uint8_t* wbuf = smem + STAGES * STAGE_BYTES + AUX_BARS;                          // DW: [2][2][WB_BUF]
-  uint64_t* wfull = tempty + 4;                                                    // DW: [half][buf]
-  uint64_t* wempty = wfull + 4;
+  uint8_t* stg = smem + PIPE_B + AUX_BARS + AUX_VEC;                  // BWDG: [2][STG_HALF]
+  uint8_t* wbuf = smem + PIPE_B + AUX_BARS;                           // DW: [2][2][WB_BUF]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -110,7 +134,7 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
     if (KIND == U_BWDG || KIND == U_DW) ptx::prefetch_tmap(&mapC);
   }
   if (warp == 1 && ptx::elect_one()) {
-    for (int i = 0; i < STAGES; ++i) {
+    for (int i = 0; i < NST; ++i) {
       ptx::mbar_init(&full[i], 1);
       ptx::mbar_init(&empty[i], 1);
     }
@@ -146,30 +170,40 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
     // ------------------------------------------------------------ TMA producer
     if (ptx::elect_one()) {
       uint32_t it = 0;
+      if (RES && (int)blockIdx.x < total) {
+        // the CTA's 128 batch rows of Xb, all of K, loaded once (grid % mt == 0)
+        const int nblk = (s.D + 63) / 64;
+        ptx::mbar_expect_tx(&wfull[0], nblk * A_BYTES);
+        for (int i = 0; i < nblk; ++i)
+          ptx::tma_load_2d(smem + i * A_BYTES, &mapA, &wfull[0], i * 64,
+                           ((int)blockIdx.x % g.mt) * BM);
+      }
       for (int u = blockIdx.x; u < total; u += gridDim.x) {
         int z, m_idx, n_idx;
         decode(u, z, m_idx, n_idx);
         const int m0 = m_idx * BM, n0 = n_idx * BN;
         const int kb0 = z * g.kb_per, kb1 = min(g.kb_total, kb0 + g.kb_per);
         for (int kb = kb0; kb < kb1; ++kb, ++it) {
-          const int st = it % STAGES;
-          const uint32_t ph = (it / STAGES) & 1;
+          const int st = it % NST;
+          const uint32_t ph = (it / NST) & 1;
           ptx::mbar_wait(&empty[st], ph ^ 1);
-          ptx::mbar_expect_tx(&full[st], STAGE_BYTES);
-          uint8_t* sA = smem + st * STAGE_BYTES;
-          uint8_t* sB = sA + A_BYTES;
-          const int k0 = kb * BK;
-          if (A_MN) {
+          ptx::mbar_expect_tx(&full[st], ST_B);
+          uint8_t* sA = pipe + st * ST_B;
+          uint8_t* sB = sA + A_ST;
+          const int k0 = kb * KB;
+          if (RES) {
+            // A is resident
+          } else if (A_MN) {
 #pragma unroll
             for (int c = 0; c < BM / 64; ++c)
-              ptx::tma_load_2d(sA + c * CHUNK_BYTES, &mapA, &full[st], m0 + c * 64, k0);
+              ptx::tma_load_2d(sA + c * CH_B, &mapA, &full[st], m0 + c * 64, k0);
           } else {
             ptx::tma_load_2d(sA, &mapA, &full[st], k0, m0);
           }
           if (B_MN) {
 #pragma unroll
             for (int c = 0; c < BN / 64; ++c)
-              ptx::tma_load_2d(sB + c * CHUNK_BYTES, &mapB, &full[st], n0 + c * 64, k0);
+              ptx::tma_load_2d(sB + c * CH_B, &mapB, &full[st], n0 + c * 64, k0);
           } else {
             ptx::tma_load_2d(sB, &mapB, &full[st], k0, n0);
           }
@@ -185,6 +219,7 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
       const uint32_t stepA = A_MN ? g.kstep_mn : 32u;
       const uint32_t stepB = B_MN ? g.kstep_mn : 32u;
       uint32_t it = 0, lt = 0;
+      if (RES && (int)blockIdx.x < total) ptx::mbar_wait(&wfull[0], 0);   // resident Xb landed
       for (int u = blockIdx.x; u < total; u += gridDim.x, ++lt) {
         const int z = u / tiles_mn;
         const int kb0 = z * g.kb_per, kb1 = min(g.kb_total, kb0 + g.kb_per);
@@ -193,14 +228,16 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + a * BN;
         for (int kb = kb0; kb < kb1; ++kb, ++it) {
-          const int st = it % STAGES;
-          const uint32_t ph = (it / STAGES) & 1;
+          const int st = it % NST;
+          const uint32_t ph = (it / NST) & 1;
           ptx::mbar_wait(&full[st], ph);
           ptx::tc_fence_after();
-          const uint32_t aA = ptx::smem_u32(smem + st * STAGE_BYTES);
-          const uint32_t aB = aA + A_BYTES;
+          // resident A: 64-wide K blocks of 16 KB; stage kb covers K = [32 kb, 32 kb + 32)
+          const uint32_t aA = RES ? ptx::smem_u32(smem + (kb >> 1) * A_BYTES) + (kb & 1) * 64u
+                                  : ptx::smem_u32(pipe + st * ST_B);
+          const uint32_t aB = ptx::smem_u32(pipe + st * ST_B) + A_ST;
 #pragma unroll
-          for (int kk = 0; kk < BK / 16; ++kk) {
+          for (int kk = 0; kk < KB / 16; ++kk) {
             ptx::umma_bf16(d_tmem, ptx::smem_desc(hiA, aA + kk * stepA),
                            ptx::smem_desc(hiB, aB + kk * stepB), idesc,
                            (kb > kb0 || kk > 0) ? 1u : 0u);
@@ -251,7 +288,7 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
       if (pu >= total) return;
       int pz, pm, pn;
       decode(pu, pz, pm, pn);
-      if (KIND == U_FWD) pre0 = s.inv_c[pn * BN + et];
+      if (IS_FWD) pre0 = s.inv_c[pn * BN + et];
       if (KIND == U_BWDG) {
         const int i = pn * BN + et;
         const bool iv = i < s.B;
@@ -313,7 +350,7 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
         process(r1, cp * 2 + 1);                           \
       }
 
-      if (KIND == U_FWD) {
+      if (IS_FWD) {
         // ---- thread = batch row, columns = classes.  Stage 1/c_j for the tile in smem.
         v0[et] = pre0;
         prefetch_tile(u + gridDim.x);
@@ -486,7 +523,7 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
       }
 #undef ASM_EPILOGUE_CHUNKS
     }
-    if (KIND == U_FWD && fwd_row >= 0)
+    if (IS_FWD && fwd_row >= 0)
       s.part[(size_t)fwd_row * s.NT + (blockIdx.x / g.mt) * 2 + half] = make_float2(run_m, run_z);
   }
 
@@ -565,6 +602,7 @@ bool umma_build_maps(UmmaMaps* m, const Step& s) {
   ok &= encode_map(&m->xb_mn, s.Xb, s.D, s.B, s.D, 64, 64);     // B of DW   (MN-major, N = d)
   // Wb [D, Cp]
   ok &= encode_map(&m->wb_mn, s.Wb, s.Cp, s.D, s.Cp, 64, 64);   // B of FWD / A of BWDG (MN-major)
+  ok &= encode_map(&m->wb_mn32, s.Wb, s.Cp, s.D, s.Cp, 64, 32); // B of FWDR (32-deep K stages)
   ok &= encode_map(&m->wb_k, s.Wb, s.Cp, s.D, s.Cp, 64, 256);   // B of DX   (K-major, N = d)
   // G'' [B, Cp]
   ok &= encode_map(&m->g_k, s.G, s.Cp, s.B, s.Cp, 64, 128);     // A of DX   (K-major, M = batch)
@@ -586,13 +624,15 @@ static UmmaArgs base_args(const UmmaTuning& tu) {
 
 cudaError_t umma_configure() {
   cudaError_t e;
-  e = cudaFuncSetAttribute(umma_kernel<U_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  e = cudaFuncSetAttribute(umma_kernel<U_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<U_FWD>::SMEM);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(umma_kernel<U_BWDG>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  e = cudaFuncSetAttribute(umma_kernel<U_FWDR>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<U_FWDR>::SMEM);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(umma_kernel<U_DW>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  e = cudaFuncSetAttribute(umma_kernel<U_BWDG>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<U_BWDG>::SMEM);
   if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(umma_kernel<U_DX>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  e = cudaFuncSetAttribute(umma_kernel<U_DW>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<U_DW>::SMEM);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(umma_kernel<U_DX>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<U_DX>::SMEM);
 }
 
 void launch_umma_forward(const Step& s, const UmmaMaps& m, const UmmaTuning& tu, int num_sms,
@@ -600,9 +640,18 @@ void launch_umma_forward(const Step& s, const UmmaMaps& m, const UmmaTuning& tu,
   UmmaArgs g = base_args(tu);   // S = Xb Wb: lanes = batch rows, columns = classes
   g.mt = (s.B + BM - 1) / BM;
   g.nt = s.Cp / BN;
+  const int grid = umma_forward_grid(s.B, s.Cp, num_sms);
+  if (s.D <= 512 && (tu.debug_flags & 4)) {   // opt-in: measured slower (55 vs 48 us at cfg 3)
+    // Xb row tile resident in shared memory, weights stream in 32-deep K stages
+    g.kb_total = (s.D + 31) / 32;
+    g.kb_per = g.kb_total;
+    g.desc_hi_mn = ptx::make_smem_desc_hi(Geo<U_FWDR>::CH_B, tu.mn_sbo);   // chunk stride 4 KB
+    umma_kernel<U_FWDR><<<grid, NUM_THREADS, Geo<U_FWDR>::SMEM, st>>>(m.xb_k, m.wb_mn32, m.wb_mn32, s, g);
+    return;
+  }
   g.kb_total = (s.D + BK - 1) / BK;
   g.kb_per = g.kb_total;
-  umma_kernel<U_FWD><<<umma_forward_grid(s.B, s.Cp, num_sms), NUM_THREADS, SMEM_BYTES, st>>>(m.xb_k, m.wb_mn, m.wb_mn, s, g);
+  umma_kernel<U_FWD><<<grid, NUM_THREADS, Geo<U_FWD>::SMEM, st>>>(m.xb_k, m.wb_mn, m.wb_mn, s, g);
 }
 
 void launch_umma_bwdg(const Step& s, const UmmaMaps& m, const UmmaTuning& tu, int num_sms,
@@ -612,7 +661,7 @@ void launch_umma_bwdg(const Step& s, const UmmaMaps& m, const UmmaTuning& tu, in
   g.nt = (s.B + BN - 1) / BN;
   g.kb_total = (s.D + BK - 1) / BK;
   g.kb_per = g.kb_total;
-  umma_kernel<U_BWDG><<<min(g.mt * g.nt, num_sms), NUM_THREADS, SMEM_BYTES, st>>>(m.wb_mn, m.xb_k256, m.g_st, s, g);
+  umma_kernel<U_BWDG><<<min(g.mt * g.nt, num_sms), NUM_THREADS, Geo<U_BWDG>::SMEM, st>>>(m.wb_mn, m.xb_k256, m.g_st, s, g);
 }
 
 void launch_umma_dw(const Step& s, const UmmaMaps& m, const UmmaTuning& tu, int num_sms,
@@ -622,7 +671,7 @@ void launch_umma_dw(const Step& s, const UmmaMaps& m, const UmmaTuning& tu, int 
   g.nt = (s.D + BN - 1) / BN;
   g.kb_total = (s.B + BK - 1) / BK;
   g.kb_per = g.kb_total;
-  umma_kernel<U_DW><<<min(g.mt * g.nt, num_sms), NUM_THREADS, SMEM_BYTES, st>>>(m.g_mn, m.xb_mn, m.wb_box, s, g);
+  umma_kernel<U_DW><<<min(g.mt * g.nt, num_sms), NUM_THREADS, Geo<U_DW>::SMEM, st>>>(m.g_mn, m.xb_mn, m.wb_box, s, g);
 }
 
 void launch_umma_dx(const Step& s, const UmmaMaps& m, const UmmaTuning& tu, int num_sms,
@@ -633,7 +682,7 @@ void launch_umma_dx(const Step& s, const UmmaMaps& m, const UmmaTuning& tu, int 
   g.kb_total = (s.Cp + BK - 1) / BK;
   g.ks = s.KS;
   g.kb_per = (g.kb_total + g.ks - 1) / g.ks;
-  umma_kernel<U_DX><<<min(g.mt * g.nt * g.ks, num_sms), NUM_THREADS, SMEM_BYTES, st>>>(m.g_k, m.wb_k, m.wb_k, s, g);
+  umma_kernel<U_DX><<<min(g.mt * g.nt * g.ks, num_sms), NUM_THREADS, Geo<U_DX>::SMEM, st>>>(m.g_k, m.wb_k, m.wb_k, s, g);
 }
 
 }  // namespace asmh
