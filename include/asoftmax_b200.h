@@ -125,6 +125,13 @@ int asm_check_labels(asm_head* h, void* cuda_stream);
 /* Number of kernels the last asm_* step call launched on its stream (for bench.py). */
 int asm_last_launch_count(const asm_head* h);
 
+/* CUDA-graph support.  Kernel arguments are frozen when a step is captured into a graph, so
+ * lambda (which anneals per step) can instead be read from a caller-owned DEVICE float:
+ * once set (non-NULL) it overrides the by-value `lambda` argument of every step call; NULL
+ * restores the by-value behaviour.  All step calls are capturable (no synchronisation, no
+ * allocation) as long as asm_check_labels / profiling are not used inside the capture. */
+int asm_set_lambda_device(asm_head* h, const float* lambda_dev);
+
 /* Per-kernel device timing for bench.py's roofline: when enabled every kernel of a step is
  * bracketed by CUDA events on the step's stream.  asm_get_profile synchronises on the last
  * event and writes up to max_n durations (ms) and 32-byte NUL-terminated kernel names;

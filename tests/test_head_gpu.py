@@ -249,3 +249,21 @@ def test_repeatable_bitwise():
     b = run_gpu(inp, 4, 5.0, "bf16")
     assert a[0] == b[0]
     assert np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3])
+
+
+def test_cuda_graph_step_matches_eager_and_follows_lambda():
+    """GraphedASoftmaxStep: same results as the eager call, lambda read from device memory."""
+    from tf_face_toolbox_b200 import GraphedASoftmaxStep
+    dev = torch.device("cuda:0")
+    inp = make_inputs(256, 512, 4000, seed=31)
+    W = inp.W.to(dev)
+    step = GraphedASoftmaxStep(W, batch_size=256, m=4, mode="bf16")
+    for lam in (5.0, 0.0, 1000 / 1.12):
+        loss_g, dX_g, dW_g = step(inp.X.pin_memory(), inp.y.pin_memory(), lam)
+        torch.cuda.synchronize()
+        loss_e, _, dX_e, dW_e = asoftmax_head(inp.X.to(dev), inp.y.to(dev), 4000, 4, lam, weights=W, mode="bf16")
+        torch.cuda.synchronize()
+        assert float(loss_g) == float(loss_e)
+        assert torch.equal(dX_g, dX_e) and torch.equal(dW_g, dW_e)
+    r = ref.asoftmax_head(inp.X.numpy(), inp.W.numpy(), inp.y.numpy(), 4, 1000 / 1.12)
+    assert abs(float(loss_g) - r.loss) <= 2e-3 * r.loss

@@ -53,6 +53,7 @@ SYMBOLS = {
     "asm_backward_partial": (C.c_int, [_P, _P, C.c_int32, _P, _P, _P, _P]),
     "asm_check_labels": (C.c_int, [_P, _P]),
     "asm_last_launch_count": (C.c_int, [_P]),
+    "asm_set_lambda_device": (C.c_int, [_P, _P]),
     "asm_set_profiling": (C.c_int, [_P, C.c_int]),
     "asm_get_profile": (C.c_int, [_P, C.c_int32, _P, _P]),
     "asm_version": (C.c_char_p, []),

@@ -431,6 +431,12 @@ int asm_forward(asm_head* h, const float* X, int32_t B, const void* labels, int3
   return run_backward(h, nullptr, 1, loss_out, nullptr, nullptr, false, stream);
 }
 
+int asm_set_lambda_device(asm_head* h, const float* lambda_dev) {
+  if (!h) return ASM_ERR_INVALID_ARG;
+  h->st.lambda_dev = lambda_dev;
+  return ASM_OK;
+}
+
 int asm_set_profiling(asm_head* h, int enable) {
   if (!h) return ASM_ERR_INVALID_ARG;
   if (enable && !h->ev[0]) {

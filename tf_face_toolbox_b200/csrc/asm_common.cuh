@@ -47,6 +47,12 @@ __device__ __forceinline__ float target_logit(float s, float n, float inv_n, int
   return (lambda * s + n * psi) / (1.0f + lambda);
 }
 
+// lambda of this step: a by-value kernel argument, or (for CUDA-graph replay, where kernel
+// arguments are frozen) a device scalar the host updates between replays
+__device__ __forceinline__ float step_lambda(float by_value, const float* dev) {
+  return dev ? __ldg(dev) : by_value;
+}
+
 // Online-softmax pair combine: (m, z) <- (m, z) (+) (m2, z2)
 __device__ __forceinline__ void ms_combine(float& m, float& z, float m2, float z2) {
   const float mn = fmaxf(m, m2);

@@ -14,6 +14,7 @@ struct Step {
   // problem
   int B, D, C, Cp, C_total, class_offset, m, mode;
   float lambda, invB;
+  const float* lambda_dev;   // optional device scalar overriding `lambda` (CUDA-graph replay)
   // caller buffers (device)
   const float* X;            // [B, D]
   const float* W;            // [D, C]

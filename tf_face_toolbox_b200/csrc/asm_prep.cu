@@ -216,8 +216,9 @@ __global__ void __launch_bounds__(256) combine_kernel(Step s, const float* stats
         const float t = fminf(1.f, fmaxf(-1.f, s.tgt_s[row] * inv_n));
         psi_eval(t, s.m, psi, dpsi);
         const float gy = (expf(s.tgt_f[row] - lse) - 1.0f) * s.invB;
-        const float il = 1.0f / (1.0f + s.lambda);
-        gt = gy * (s.lambda + dpsi) * il;
+        const float lam = step_lambda(s.lambda, s.lambda_dev);
+        const float il = 1.0f / (1.0f + lam);
+        gt = gy * (lam + dpsi) * il;
         r = gy * (psi - t * dpsi) * il * inv_n;
       }
       s.gtarget[row] = gt;

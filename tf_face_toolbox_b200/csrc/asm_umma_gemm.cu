@@ -385,7 +385,8 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
             float sv = 0.f;
 #pragma unroll
             for (int b = 0; b < 32; ++b) sv = sel_eq(b, bsel, v[b], sv);
-            const float fv = fwd_target(s.tgt_s, s.tgt_f, s.n, s.inv_n, s.m, s.lambda, row, sv);
+            const float fv = fwd_target(s.tgt_s, s.tgt_f, s.n, s.inv_n, s.m,
+                                        step_lambda(s.lambda, s.lambda_dev), row, sv);
 #pragma unroll
             for (int b = 0; b < 32; ++b) v[b] = sel_eq(b, bsel, fv, v[b]);
           }

@@ -101,11 +101,13 @@ def _round_batch(B: int) -> int:
     return max(128, (B + 127) // 128 * 128)
 
 
-def get_handle(device, D, C_total, C_local, class_offset, B, m, mode, rank=0, world=1) -> _Handle:
+def get_handle(device, D, C_total, C_local, class_offset, B, m, mode, rank=0, world=1, tag=None) -> _Handle:
+    """`tag` separates handles with different per-handle state (e.g. a CUDA-graph step that
+    reads lambda from device memory) from the plain eager ones."""
     device = torch.device(device)
     if device.index is None:
         device = torch.device("cuda", torch.cuda.current_device())
-    key = (device.index, D, C_total, C_local, class_offset, _round_batch(B), m, mode, rank, world)
+    key = (device.index, D, C_total, C_local, class_offset, _round_batch(B), m, mode, rank, world, tag)
     h = _HANDLES.get(key)
     if h is None:
         h = _Handle(device, D, C_total, C_local, class_offset, _round_batch(B), m, mode, rank, world)
@@ -137,7 +139,7 @@ def _check_inputs(embeddings, labels, weights, num_classes):
 def asoftmax_head(embeddings: torch.Tensor, labels: torch.Tensor, num_classes: int, m: int = 4,
                   lambda_state=None, *, weights: torch.Tensor, mode: str = "bf16",
                   return_logits: bool = False, compute_grads: bool = True,
-                  check_labels: bool = False
+                  check_labels: bool = False, _handle_tag=None
                   ) -> Tuple[torch.Tensor, Optional[torch.Tensor], Optional[torch.Tensor], Optional[torch.Tensor]]:
     """A-softmax head forward + backward on one GPU that owns every class.
 
@@ -155,7 +157,7 @@ def asoftmax_head(embeddings: torch.Tensor, labels: torch.Tensor, num_classes: i
     y = labels.contiguous()
     B, D = X.shape
     Cn = W.shape[1]
-    h = get_handle(X.device, D, Cn, Cn, 0, B, m, mode)
+    h = get_handle(X.device, D, Cn, Cn, 0, B, m, mode, tag=_handle_tag)
     lam = _as_lambda(lambda_state)
     loss = torch.empty(1, device=X.device, dtype=torch.float32)
     logits = torch.empty(B, Cn, device=X.device, dtype=torch.float32) if return_logits else None
@@ -182,6 +184,61 @@ def asoftmax_head(embeddings: torch.Tensor, labels: torch.Tensor, num_classes: i
 def last_launch_count(device, D, C_total, B, m, mode) -> int:
     h = get_handle(device, D, C_total, C_total, 0, B, m, mode)
     return int(h.lib.asm_last_launch_count(h.ptr))
+
+
+# --------------------------------------------------------------------------------------
+# CUDA-graph step: the whole head (7 launches, fork/join included) replayed as one graph
+# --------------------------------------------------------------------------------------
+class GraphedASoftmaxStep:
+    """One fixed-shape A-softmax step captured into a CUDA graph.
+
+        step = GraphedASoftmaxStep(weights, batch_size=512, m=4, mode="bf16")
+        loss, dX, dW = step(embeddings, labels, lambda_state)     # copies inputs, replays
+
+    Inputs are copied into static device buffers (so host tensors in pinned memory are fine);
+    lambda lives in a device scalar the kernels read (asm_set_lambda_device), because kernel
+    arguments are frozen at capture.  `weights` is used in place: update it in place
+    (optimizer step), never rebind it.  Outputs are static tensors overwritten by each replay.
+    """
+
+    def __init__(self, weights: torch.Tensor, batch_size: int, m: int = 4, mode: str = "bf16",
+                 labels_dtype=torch.int32):
+        assert weights.is_cuda and weights.dtype == torch.float32 and weights.is_contiguous()
+        dev = weights.device
+        self.W = weights
+        D, Cn = weights.shape
+        self.X = torch.zeros(batch_size, D, device=dev, dtype=torch.float32)
+        self.y = torch.zeros(batch_size, device=dev, dtype=labels_dtype)
+        self.lam = torch.zeros(1, device=dev, dtype=torch.float32)
+        self._lam_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+        self.m, self.mode, self.Cn = m, mode, Cn
+        self._tag = ("graph", id(self))
+        h = get_handle(dev, D, Cn, Cn, 0, batch_size, m, mode, tag=self._tag)
+        _lib.check(h.lib.asm_set_lambda_device(h.ptr, self.lam.data_ptr()), h.ptr)
+        cur = torch.cuda.current_stream(dev)
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):          # warm-up outside capture (builds the TMA maps)
+            for _ in range(2):
+                self._run()
+        cur.wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss, self.dX, self.dW = self._run()
+
+    def _run(self):
+        loss, _, dX, dW = asoftmax_head(self.X, self.y, self.Cn, self.m, 0.0, weights=self.W,
+                                        mode=self.mode, _handle_tag=self._tag)
+        return loss, dX, dW
+
+    def __call__(self, embeddings: torch.Tensor, labels: torch.Tensor, lambda_state=None):
+        self._lam_host[0] = _as_lambda(lambda_state)
+        self.lam.copy_(self._lam_host, non_blocking=True)
+        self.X.copy_(embeddings, non_blocking=True)
+        self.y.copy_(labels, non_blocking=True)
+        self.graph.replay()
+        return self.loss, self.dX, self.dW
 
 
 # --------------------------------------------------------------------------------------

@@ -39,10 +39,15 @@ class _CudaShard:
     def __init__(self, D, C_total, lo, hi, m, mode, rank, world, device):
         self.args = (D, C_total, hi - lo, lo, m, mode, rank, world)
         self.device = torch.device(device)
+        self.tag = None
+        self.lambda_dev = None      # device scalar read by the kernels (CUDA-graph replay)
 
     def _handle(self, B):
         D, C_total, C_local, lo, m, mode, rank, world = self.args
-        return get_handle(self.device, D, C_total, C_local, lo, B, m, mode, rank, world)
+        h = get_handle(self.device, D, C_total, C_local, lo, B, m, mode, rank, world, tag=self.tag)
+        if self.lambda_dev is not None:
+            _lib.check(h.lib.asm_set_lambda_device(h.ptr, self.lambda_dev.data_ptr()), h.ptr)
+        return h
 
     def forward_partial(self, X, y, W, lam):
         B = X.shape[0]
@@ -126,6 +131,40 @@ class ShardedASoftmaxHead:
         loss, dX_partial, dW = self.compute.backward_partial(stats_all, X, self.weights)
         dX_local = self._reduce_scatter_rows(dX_partial, b)
         return loss, dX_local, dW
+
+    # ---- CUDA-graph replay of the whole sharded step (collectives included) --------------
+    def capture(self, batch_local: int, labels_dtype=torch.int32):
+        """Capture step() for a fixed local batch into a CUDA graph.  Afterwards
+        `step_graphed(X_local, y_local, lam)` copies the inputs into static buffers and
+        replays: one graph launch instead of 3 collectives + 11 kernel launches."""
+        dev = self.device
+        self._gX = torch.zeros(batch_local, self.D, device=dev, dtype=torch.float32)
+        self._gy = torch.zeros(batch_local, device=dev, dtype=labels_dtype)
+        self._glam = torch.zeros(1, device=dev, dtype=torch.float32)
+        self._glam_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+        self.compute.tag = ("graph", id(self))
+        self.compute.lambda_dev = self._glam
+        cur = torch.cuda.current_stream(dev)
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                self.step(self._gX, self._gy, 0.0)
+        cur.wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self._gout = self.step(self._gX, self._gy, 0.0)
+        return self
+
+    def step_graphed(self, embeddings_local, labels_local, lambda_state=None):
+        lam = _as_lambda(lambda_state) if lambda_state is not None else self.lambda_state.step()
+        self._glam_host[0] = lam
+        self._glam.copy_(self._glam_host, non_blocking=True)
+        self._gX.copy_(embeddings_local, non_blocking=True)
+        self._gy.copy_(labels_local, non_blocking=True)
+        self._graph.replay()
+        return self._gout
 
     def gather_weights(self) -> torch.Tensor:
         """All shards -> one [D, C] fp32 tensor (`classifier/fc_classifier/weights`, the
