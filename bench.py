@@ -180,6 +180,7 @@ def run_ours(args, cfg):
     B, D, Cn, mode = cfg["B"], cfg["D"], cfg["C"], args.mode
     K, Wm = args.steps, args.warmup
     peaks = load_peaks()
+    t_start = time.time()
     inp = make_inputs(B, D, Cn)
     flush = None
     need_flush = Cn * D * 4 <= 126e6
@@ -211,7 +212,8 @@ def run_ours(args, cfg):
     # the public GraphedASoftmaxStep / ShardedASoftmaxHead.capture API.  Falls back to the
     # eager call if capture is not possible.
     graphed = None
-    if not args.no_graph:
+    # multi-rank capture (NCCL collectives inside the graph) is opt-in: --graph
+    if not args.no_graph and (world == 1 or args.graph):
         try:
             if world == 1:
                 gstep = GraphedASoftmaxStep(Wd, batch_size=B, m=M_MARGIN, mode=mode)
@@ -267,6 +269,10 @@ def run_ours(args, cfg):
         torch.cuda.synchronize()
         flush_ms = e0.elapsed_time(e1) / 20
 
+    def note(msg):
+        if rank == 0 and os.environ.get("BENCH_VERBOSE"):
+            print(f"[bench {time.time() - t_start:6.1f}s] {msg}", file=sys.stderr, flush=True)
+    note("setup done, graph=%s" % (graphed is not None))
     # ---- (1) device-resident timing: the headline `value`
     for _ in range(max(Wm, 3)):
         run_step()
@@ -275,6 +281,7 @@ def run_ours(args, cfg):
     ms_step = ms_total / K - flush_ms
     value = B / (ms_step * 1e-3)
 
+    note("value loop done: %.4f ms/step" % ms_step)
     # ---- (2) per-kernel durations (CUDA events on the launching stream, inside the library)
     kernels = {}
     h = get_handle(dev, D, Cn, Cn, 0, B, M_MARGIN, mode) if world == 1 else head.compute._handle(B)
@@ -293,6 +300,7 @@ def run_ours(args, cfg):
     h.lib.asm_set_profiling(h.ptr, 0)
     kavg = {k: sum(v) / len(v) for k, v in kernels.items()}
 
+    note("profile loop done")
     # ---- (3) end to end through the public Python API with HOST buffers
     Xh = (inp.X if world == 1 else inp.X[rank * b_local:(rank + 1) * b_local]).contiguous().pin_memory()
     yh = (inp.y if world == 1 else inp.y[rank * b_local:(rank + 1) * b_local]).contiguous().pin_memory()
@@ -316,6 +324,7 @@ def run_ours(args, cfg):
         for _ in range(3):
             fn()
         e2e_ms[name] = timed(fn, K) / K - flush_ms
+    note("e2e loops done")
     e2e_path = min(e2e_ms, key=e2e_ms.get)
     ms_e2e = e2e_ms[e2e_path]
     t_load1 = time.time()
@@ -402,6 +411,7 @@ def main():
     ap.add_argument("--mode", default=None, choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time the eager per-kernel launches")
+    ap.add_argument("--graph", action="store_true", help="N>1: capture the sharded step (with its collectives) into a CUDA graph")
     args = ap.parse_args()
     cfg = dict(CONFIGS[args.workload])
     if args.mode is None:

@@ -142,19 +142,28 @@ class ShardedASoftmaxHead:
         self._gy = torch.zeros(batch_local, device=dev, dtype=labels_dtype)
         self._glam = torch.zeros(1, device=dev, dtype=torch.float32)
         self._glam_host = torch.zeros(1, dtype=torch.float32).pin_memory()
-        self.compute.tag = ("graph", id(self))
-        self.compute.lambda_dev = self._glam
-        cur = torch.cuda.current_stream(dev)
-        side = torch.cuda.Stream(dev)
-        side.wait_stream(cur)
-        with torch.cuda.stream(side):
-            for _ in range(3):
-                self.step(self._gX, self._gy, 0.0)
-        cur.wait_stream(side)
-        torch.cuda.synchronize(dev)
-        self._graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self._graph):
-            self._gout = self.step(self._gX, self._gy, 0.0)
+        # a dedicated shard-compute object (own handle / workspace) whose kernels read lambda
+        # from the device scalar; the eager step() keeps its own by-value handle
+        eager_compute = self.compute
+        gcompute = _CudaShard(self.D, self.C, self.lo, self.hi, self.m, self.mode, self.rank,
+                              self.world, self.device)
+        gcompute.tag = ("graph", id(self))
+        gcompute.lambda_dev = self._glam
+        self.compute = gcompute
+        try:
+            cur = torch.cuda.current_stream(dev)
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    self.step(self._gX, self._gy, 0.0)
+            cur.wait_stream(side)
+            torch.cuda.synchronize(dev)
+            self._graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph):
+                self._gout = self.step(self._gX, self._gy, 0.0)
+        finally:
+            self.compute = eager_compute
         return self
 
     def step_graphed(self, embeddings_local, labels_local, lambda_state=None):
