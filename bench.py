@@ -174,8 +174,12 @@ def run_ours(args, cfg):
         raise SystemExit("bench.py: no CUDA device; the A-softmax head has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # a stuck collective must not hang the caller: dump every thread's stack and exit
+    import faulthandler
+    faulthandler.dump_traceback_later(float(os.environ.get("BENCH_WATCHDOG_S", "900")), exit=True)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "WARN")      # keep stdout to the one JSON line
+        os.environ["NCCL_DEBUG"] = os.environ.get("BENCH_NCCL_DEBUG", "WARN")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     B, D, Cn, mode = cfg["B"], cfg["D"], cfg["C"], args.mode
     K, Wm = args.steps, args.warmup
@@ -341,9 +345,12 @@ def run_ours(args, cfg):
         done += 50
         torch.cuda.synchronize()
     t_load1 = time.time()
+    note("extra-load loop done (%d steps)" % n_extra)
     clocks = sampler.stop(t_load0, t_load1) if rank == 0 else None
+    note("clock sampler stopped")
     if world > 1:
         dist.barrier()
+    note("final barrier passed")
 
     if rank == 0:
         C_local = Cn if world == 1 else -(-Cn // world)
