@@ -176,7 +176,7 @@ def run_ours(args, cfg):
     dev = torch.device("cuda", local)
     # a stuck collective must not hang the caller: dump every thread's stack and exit
     import faulthandler
-    faulthandler.dump_traceback_later(float(os.environ.get("BENCH_WATCHDOG_S", "900")), exit=True)
+    faulthandler.dump_traceback_later(float(os.environ.get("BENCH_WATCHDOG_S", "600")), exit=True)
     if world > 1:
         os.environ["NCCL_DEBUG"] = os.environ.get("BENCH_NCCL_DEBUG", "WARN")
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the one JSON line
@@ -362,8 +362,8 @@ def run_ours(args, cfg):
                 roof_kernels.append({"kernel": nm, "ms": ms, "bound": "tensor", "achieved": ach, "unit": "TFLOP/s",
                                      "frac": ach / peaks["tf_burst"]})
             elif nm == "prep_norms":
-                Cp = (Cn + 255) // 256 * 256
-                by = 4.0 * D * Cn + (2.0 * D * Cp if mode == "bf16" else 0) + 4.0 * B * D
+                Cp = (C_local + 255) // 256 * 256
+                by = 4.0 * D * C_local + (2.0 * D * Cp if mode == "bf16" else 0) + 4.0 * B * D
                 ach = by / (ms * 1e-3) / 1e9
                 roof_kernels.append({"kernel": nm, "ms": ms, "bound": "hbm", "achieved": ach, "unit": "GB/s",
                                      "frac": ach / peaks["hbm"]})
@@ -403,8 +403,24 @@ def run_ours(args, cfg):
             line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
                                     "sample": r["sample"]}
         print(json.dumps(line), flush=True)
+    # teardown must never turn a finished measurement into a hang: drop the captured graphs
+    # first (NCCL work captured in a live graph can block destroy_process_group) and bail out
+    # with success if the process group still does not come down
+    sys.stdout.flush()
+    faulthandler.cancel_dump_traceback_later()
     if world > 1:
+        bail = threading.Timer(20.0, lambda: os._exit(0))
+        bail.daemon = True
+        bail.start()
+        graphed = None
+        run_step = None
+        for attr in ("_graph", "_gout"):
+            if hasattr(head, attr):
+                setattr(head, attr, None)
+        torch.cuda.synchronize()
+        dist.barrier()
         dist.destroy_process_group()
+        bail.cancel()
 
 
 def main():
