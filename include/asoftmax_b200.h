@@ -125,6 +125,27 @@ int asm_check_labels(asm_head* h, void* cuda_stream);
 /* Number of kernels the last asm_* step call launched on its stream (for bench.py). */
 int asm_last_launch_count(const asm_head* h);
 
+/*
+ * Fused classifier optimizer.  Replaces, for the classifier
+ * variable, `opt.apply_gradients(grads)` of data_parallel.py:186-196 --
+ * MomentumOptimizer(lr, momentum=0.9) or AdamOptimizer(lr, beta1=0.5, beta2=0.999) -- applied to
+ * the gradient of cross_entropy + reg_loss (L2 regulariser wd * 0.5 * |W|^2, nets/sphere.py:88).
+ * While an optimizer is armed (kind != ASM_OPT_NONE) every step call UPDATES `W` IN PLACE in the
+ * epilogue of the dW kernel (the `const` on W is waived), `dW` is not written and may be NULL,
+ * and state0 / state1 ([D, C_local] fp32, caller-owned, zero-initialised by the caller) hold the
+ * momentum accumulator, or Adam's m and v.  Pass opt == NULL or kind == ASM_OPT_NONE to disarm.
+ *   momentum: accum = momentum*accum + g;  W -= lr*accum              (g = dW + wd*W)
+ *   adam:     m = b1*m + (1-b1)*g;  v = b2*v + (1-b2)*g*g;
+ *             W -= lr*sqrt(1-b2^t)/(1-b1^t) * m/(sqrt(v)+eps),  t = opt->step (from 1)
+ */
+enum { ASM_OPT_NONE = 0, ASM_OPT_MOMENTUM = 1, ASM_OPT_ADAM = 2 };
+typedef struct {
+  int32_t kind;
+  float   lr, momentum, beta1, beta2, epsilon, weight_decay;
+  int64_t step;
+} asm_optimizer;
+int asm_set_optimizer(asm_head* h, const asm_optimizer* opt, float* state0, float* state1);
+
 /* CUDA-graph support.  Kernel arguments are frozen when a step is captured into a graph, so
  * lambda (which anneals per step) can instead be read from a caller-owned DEVICE float:
  * once set (non-NULL) it overrides the by-value `lambda` argument of every step call; NULL

@@ -203,3 +203,23 @@ def sharded_combine(stats):
     M = ms.max(axis=0)
     Z = (zs * np.exp(ms - M)).sum(axis=0)
     return M, np.log(Z), float(np.mean(np.log(Z) + M - fy))
+
+
+# --------------------------------------------------------------------------------------
+# classifier optimizer step (data_parallel.py:186-196) on the L2-regularised gradient
+# --------------------------------------------------------------------------------------
+def optimizer_step(W, dW, state0, state1, kind="momentum", lr=0.1, momentum=0.9, beta1=0.5,
+                   beta2=0.999, epsilon=1e-8, weight_decay=5e-4, step=1):
+    """Returns (W_new, state0_new, state1_new).  TF semantics: MomentumOptimizer
+    (accum = momentum*accum + g; var -= lr*accum) and AdamOptimizer
+    (lr_t = lr*sqrt(1-b2^t)/(1-b1^t); var -= lr_t*m/(sqrt(v)+eps)); g = dW + wd*W is the
+    gradient of cross_entropy + reg_loss (nets/net_base.py:103-107, nets/sphere.py:88)."""
+    W = np.asarray(W, dtype=np.float64)
+    g = np.asarray(dW, dtype=np.float64) + weight_decay * W
+    if kind == "momentum":
+        s0 = momentum * np.asarray(state0, dtype=np.float64) + g
+        return W - lr * s0, s0, None
+    m = beta1 * np.asarray(state0, dtype=np.float64) + (1 - beta1) * g
+    v = beta2 * np.asarray(state1, dtype=np.float64) + (1 - beta2) * g * g
+    lr_t = lr * math.sqrt(1 - beta2 ** step) / (1 - beta1 ** step)
+    return W - lr_t * m / (np.sqrt(v) + epsilon), m, v

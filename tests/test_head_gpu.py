@@ -267,3 +267,44 @@ def test_cuda_graph_step_matches_eager_and_follows_lambda():
         assert torch.equal(dX_g, dX_e) and torch.equal(dW_g, dW_e)
     r = ref.asoftmax_head(inp.X.numpy(), inp.W.numpy(), inp.y.numpy(), 4, 1000 / 1.12)
     assert abs(float(loss_g) - r.loss) <= 2e-3 * r.loss
+
+
+@pytest.mark.parametrize("kind", ["Momentum", "Adam"])
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_fused_optimizer_matches_unfused_update(kind, mode):
+    """§8f-1: the optimizer fused into the dW epilogue equals grad-then-update over 3 steps
+    (TF Momentum / Adam semantics on cross_entropy + L2 reg_loss, data_parallel.py:186-196)."""
+    from tf_face_toolbox_b200 import FusedOptimizer
+    dev = torch.device("cuda:0")
+    B, D, Cn = 128, 128, 3000
+    inp = make_inputs(B, D, Cn, seed=41)
+    lr = 0.05 if kind == "Momentum" else 1e-3
+    W_f = inp.W.to(dev).clone()
+    opt = FusedOptimizer(kind, lr=lr, weight_decay=5e-4)
+    Wr = inp.W.double().numpy().copy()
+    s0 = np.zeros_like(Wr)
+    s1 = np.zeros_like(Wr)
+    X, y = inp.X.to(dev), inp.y.to(dev)
+    for step in range(1, 4):
+        # reference: gradient from the (already parity-tested) unfused call on the same weights
+        Wcur = torch.from_numpy(Wr).float().to(dev)
+        _, _, _, dW = asoftmax_head(X, y, Cn, 4, 5.0, weights=Wcur, mode=mode)
+        Wr32 = Wcur.double().cpu().numpy()
+        Wr, s0, s1n = ref.optimizer_step(Wr32, dW.double().cpu().numpy(), s0, s1, kind.lower(), lr=lr, step=step)
+        s1 = s1n if s1n is not None else s1
+        loss, _, dX, dW_none = asoftmax_head(X, y, Cn, 4, 5.0, weights=W_f, mode=mode, optimizer=opt)
+        assert dW_none is None and np.isfinite(float(loss))
+        torch.cuda.synchronize()
+        upd_f = (W_f.double().cpu().numpy() - inp.W.double().numpy())
+        upd_r = (Wr - inp.W.double().numpy())
+        # Adam's m/sqrt(v) is sign-like on its first steps, which amplifies the bf16-vs-fp32
+        # projection difference on near-zero gradient entries
+        cos_min = 0.999 if (kind == "Adam" and mode == "bf16") else 0.9999
+        assert cosine(upd_f, upd_r) >= cos_min, (step, cosine(upd_f, upd_r))
+        # fp32: same arithmetic up to rounding.  bf16: the fused epilogue projects with the fp32
+        # master weight, the unfused one with its bf16 copy (2^-9 relative on that term)
+        tol = 2e-3 if mode == "fp32" else (3e-2 if kind == "Momentum" else 2.0)
+        np.testing.assert_allclose(upd_f, upd_r, rtol=0, atol=tol * np.abs(upd_r).max())
+    # the plain path is unaffected afterwards (optimizer disarmed): dW is returned again
+    _, _, _, dW2 = asoftmax_head(X, y, Cn, 4, 5.0, weights=W_f, mode=mode)
+    assert dW2 is not None

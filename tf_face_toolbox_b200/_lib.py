@@ -33,6 +33,15 @@ class AsmConfig(C.Structure):
     ]
 
 
+class AsmOptimizer(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("lr", C.c_float), ("momentum", C.c_float), ("beta1", C.c_float),
+                ("beta2", C.c_float), ("epsilon", C.c_float), ("weight_decay", C.c_float),
+                ("step", C.c_int64)]
+
+
+OPT_NONE, OPT_MOMENTUM, OPT_ADAM = 0, 1, 2
+
+
 class AsmError(RuntimeError):
     def __init__(self, code: int, msg: str):
         super().__init__(f"asoftmax_b200 error {code}: {msg}")
@@ -53,6 +62,7 @@ SYMBOLS = {
     "asm_backward_partial": (C.c_int, [_P, _P, C.c_int32, _P, _P, _P, _P]),
     "asm_check_labels": (C.c_int, [_P, _P]),
     "asm_last_launch_count": (C.c_int, [_P]),
+    "asm_set_optimizer": (C.c_int, [_P, C.POINTER(AsmOptimizer), _P, _P]),
     "asm_set_lambda_device": (C.c_int, [_P, _P]),
     "asm_set_profiling": (C.c_int, [_P, C.c_int]),
     "asm_get_profile": (C.c_int, [_P, C.c_int32, _P, _P]),

@@ -222,6 +222,7 @@ int run_backward(asm_head* h, const float* stats_all, int n_shards, float* loss_
   s.loss = loss_out;
   s.dX = dX;
   s.dW = dW;
+  s.Wmut = const_cast<float*>(s.W);       // only written when an optimizer is armed
   const bool tc = h->cfg.mode == ASM_MODE_BF16;
   if (stats_all) {
     // profiling: the gap between the two halves is the host-side statistics all-gather
@@ -400,7 +401,7 @@ int asm_backward_partial(asm_head* h, const float* stats_all, int32_t n_shards, 
   if (!h) return ASM_ERR_INVALID_ARG;
   if (!h->fwd_valid)
     return fail(h, ASM_ERR_INVALID_ARG, "asm_backward_partial without asm_forward_partial%s", "");
-  if (!stats_all || n_shards < 1 || !dX_partial || !dW)
+  if (!stats_all || n_shards < 1 || !dX_partial || (!dW && h->st.opt.kind == 0))
     return fail(h, ASM_ERR_INVALID_ARG, "null pointer / bad n_shards%s", "");
   return run_backward(h, stats_all, n_shards, loss_out, dX_partial, dW, true,
                       (cudaStream_t)cuda_stream);
@@ -415,7 +416,8 @@ int asm_forward_backward(asm_head* h, const float* X, int32_t B, const void* lab
                 "asm_forward_backward needs a shard that owns every class; use the partial calls%s", "");
   int rc = run_forward(h, X, B, labels, label_bytes, W, lambda, logits_out_or_null, false, stream);
   if (rc != ASM_OK) return rc;
-  if (!loss_out || !dX || !dW) return fail(h, ASM_ERR_INVALID_ARG, "null output pointer%s", "");
+  if (!loss_out || !dX || (!dW && h->st.opt.kind == 0))
+    return fail(h, ASM_ERR_INVALID_ARG, "null output pointer%s", "");
   return run_backward(h, nullptr, 1, loss_out, dX, dW, true, stream);
 }
 
@@ -429,6 +431,37 @@ int asm_forward(asm_head* h, const float* X, int32_t B, const void* labels, int3
   if (rc != ASM_OK) return rc;
   if (!loss_out) return fail(h, ASM_ERR_INVALID_ARG, "loss_out is NULL%s", "");
   return run_backward(h, nullptr, 1, loss_out, nullptr, nullptr, false, stream);
+}
+
+int asm_set_optimizer(asm_head* h, const asm_optimizer* opt, float* state0, float* state1) {
+  if (!h) return ASM_ERR_INVALID_ARG;
+  Step& s = h->st;
+  if (!opt || opt->kind == ASM_OPT_NONE) {
+    s.opt.kind = 0;
+    s.opt_s0 = s.opt_s1 = nullptr;
+    return ASM_OK;
+  }
+  if (opt->kind != ASM_OPT_MOMENTUM && opt->kind != ASM_OPT_ADAM)
+    return fail(h, ASM_ERR_INVALID_ARG, "unknown optimizer kind%s", "");
+  if (!state0 || (opt->kind == ASM_OPT_ADAM && !state1))
+    return fail(h, ASM_ERR_INVALID_ARG, "optimizer state buffer is NULL%s", "");
+  if (opt->kind == ASM_OPT_ADAM && opt->step < 1)
+    return fail(h, ASM_ERR_INVALID_ARG, "adam needs step >= 1%s", "");
+  s.opt.kind = opt->kind;
+  s.opt.mu = opt->momentum;
+  s.opt.b1 = opt->beta1;
+  s.opt.b2 = opt->beta2;
+  s.opt.eps = opt->epsilon;
+  s.opt.wd = opt->weight_decay;
+  s.opt.lr = opt->lr;
+  if (opt->kind == ASM_OPT_ADAM) {
+    const double t = (double)opt->step;
+    s.opt.lr = (float)((double)opt->lr * sqrt(1.0 - pow((double)opt->beta2, t)) /
+                       (1.0 - pow((double)opt->beta1, t)));
+  }
+  s.opt_s0 = state0;
+  s.opt_s1 = state1;
+  return ASM_OK;
 }
 
 int asm_set_lambda_device(asm_head* h, const float* lambda_dev) {

@@ -8,6 +8,32 @@
 namespace asmh {
 
 // Everything one step needs; filled by the host API (asm_api.cu), passed by value.
+// Fused classifier optimizer (asm_set_optimizer): the update the reference applies with
+// MomentumOptimizer(lr, 0.9) / AdamOptimizer(lr, beta1=0.5, beta2=0.999)
+// (data_parallel.py:186-196) to the L2-regularised gradient (nets/sphere.py:88), executed in
+// the epilogue of the dW kernel so that dW never goes to HBM.
+struct OptParams {
+  int kind;                  // 0 = off, 1 = momentum, 2 = adam
+  float lr;                  // momentum: lr; adam: lr * sqrt(1 - b2^t) / (1 - b1^t)
+  float mu, b1, b2, eps, wd;
+};
+__host__ __device__ inline void opt_apply(const OptParams& o, float grad, float& w, float& s0,
+                                          float& s1) {
+  const float g = grad + o.wd * w;               // + d(reg_loss)/dw = wd * w
+  if (o.kind == 1) {
+    s0 = o.mu * s0 + g;                          // accum = momentum * accum + grad
+    w -= o.lr * s0;                              // var  -= lr * accum
+  } else {
+    s0 = o.b1 * s0 + (1.0f - o.b1) * g;
+    s1 = o.b2 * s1 + (1.0f - o.b2) * g * g;
+#ifdef __CUDA_ARCH__
+    w -= o.lr * s0 / (sqrtf(s1) + o.eps);
+#else
+    w -= o.lr * s0 / (sqrtf(s1) + o.eps);
+#endif
+  }
+}
+
 constexpr int kRowTileHost = 128;   // == asmh::kRowTile (asm_common.cuh)
 
 struct Step {
@@ -46,6 +72,10 @@ struct Step {
   int KS;
   __nv_bfloat16* Xb;         // [B, D]    bf16 mode
   __nv_bfloat16* Wb;         // [D, Cp]   bf16 mode
+  OptParams opt;             // fused optimizer (kind 0 = off: dW is written instead)
+  float* Wmut;               // [D, C]  W, updated in place when opt.kind != 0
+  float* opt_s0;             // [D, C]  momentum accumulator / adam m
+  float* opt_s1;             // [D, C]  adam v
 };
 
 // prep: column norms of W (+ bf16 copy), row norms of X (+ bf16 copy), label localisation
@@ -92,7 +122,7 @@ void launch_umma_forward(const Step& s, const UmmaMaps& m, const UmmaTuning& tu,
 void launch_umma_bwdg(const Step& s, const UmmaMaps& m, const UmmaTuning& tu, int num_sms,
                       cudaStream_t st);
 void launch_umma_dw(const Step& s, const UmmaMaps& m, const UmmaTuning& tu, int num_sms,
-                    cudaStream_t st);
+                    cudaStream_t st);   // dW, or the fused optimizer update when s.opt.kind != 0
 void launch_umma_dx(const Step& s, const UmmaMaps& m, const UmmaTuning& tu, int num_sms,
                     cudaStream_t st);
 

@@ -49,7 +49,8 @@ constexpr float LOG2E = 1.4426950408889634f;
 // cuts the L2 -> SM operand traffic by a third.  Measured SLOWER than the streaming kernel
 // (55 vs 48 us at cfg 3): the pipeline is bound by bytes in flight (80 KB vs 192 KB), not by
 // L2 bandwidth.  Kept behind ASM_UMMA_DEBUG bit 2 as the record of that experiment.
-enum { U_FWD = 0, U_BWDG = 1, U_DW = 2, U_DX = 3, U_FWDR = 4 };
+// U_DWOPT is the dW kernel with the classifier optimizer fused into its epilogue.
+enum { U_FWD = 0, U_BWDG = 1, U_DW = 2, U_DX = 3, U_FWDR = 4, U_DWOPT = 5 };
 
 // pipeline geometry per kernel kind
 template <int KIND> struct Geo {
@@ -105,9 +106,10 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
   constexpr bool RES = G_::RES;
   constexpr int KB = G_::KB, NST = G_::NST, A_ST = G_::A_ST, ST_B = G_::ST_B;
   constexpr int RES_B = G_::RES_B, CH_B = G_::CH_B, PIPE_B = G_::PIPE_B;
-  constexpr bool A_MN = (KIND == U_BWDG || KIND == U_DW);
-  constexpr bool B_MN = (IS_FWD || KIND == U_DW);
-  constexpr bool N_FAST = (KIND == U_BWDG || KIND == U_DW);   // tile order: n index fastest
+  constexpr bool IS_DW = (KIND == U_DW || KIND == U_DWOPT);
+  constexpr bool A_MN = (KIND == U_BWDG || IS_DW);
+  constexpr bool B_MN = (IS_FWD || IS_DW);
+  constexpr bool N_FAST = (KIND == U_BWDG || IS_DW);   // tile order: n index fastest
   extern __shared__ uint8_t smem_raw[];
   // align to 1024 B (SWIZZLE_128B atoms) by adding an integer offset, so that the compiler
   // keeps the shared address space (ld.shared, not generic loads) for everything below
@@ -296,7 +298,7 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
         pre1 = iv ? __int_as_float(s.ylocal[i]) : __int_as_float(-1);
         pre2 = iv ? s.gtarget[i] : 0.f;
       }
-      if (KIND == U_DW) {
+      if (IS_DW) {
         // raw loads only (no arithmetic here, so nothing waits on them until the next tile)
         const int pj = pm * BM + lane_row;
         const float* qp = s.q_part + pj;
@@ -505,6 +507,42 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
           }
         };
         ASM_EPILOGUE_CHUNKS(process)
+      } else if (KIND == U_DWOPT) {
+        // ---- fused optimizer: thread = class j, columns = d.  The gradient element
+        // dW[d][j] = acc - W[d][j] q_j / c_j^2 (fp32 master weight) is consumed on the spot:
+        // W and the optimizer state are read, updated and written back, dW never exists.
+        const int j = m0 + lane_row;
+        const bool jv = j < s.C;
+        const float coef = -(((pre0 + pre1) + (pre3 + pre4)) + pre5) * pre2 * pre2;
+        prefetch_tile(u + gridDim.x);
+        const int d_first = n0 + col0;
+        const OptParams op = s.opt;
+        ptx::mbar_wait(&tfull[a], aph);
+        ptx::tc_fence_after();
+        auto process = [&](const uint32_t (&r)[32], int c) {
+          const int db = d_first + c * 32;
+          if (!jv || db >= s.D) return;
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {                   // 16 columns at a time
+            const size_t base = (size_t)(db + hf * 16) * s.C + j;
+            float w[16], s0[16], s1[16];
+#pragma unroll
+            for (int b = 0; b < 16; ++b) {
+              w[b] = s.Wmut[base + (size_t)b * s.C];
+              s0[b] = s.opt_s0[base + (size_t)b * s.C];
+              s1[b] = op.kind == 2 ? s.opt_s1[base + (size_t)b * s.C] : 0.f;
+            }
+#pragma unroll
+            for (int b = 0; b < 16; ++b) {
+              const float grad = fmaf(w[b], coef, __uint_as_float(r[hf * 16 + b]));
+              opt_apply(op, grad, w[b], s0[b], s1[b]);
+              s.Wmut[base + (size_t)b * s.C] = w[b];
+              s.opt_s0[base + (size_t)b * s.C] = s0[b];
+              if (op.kind == 2) s.opt_s1[base + (size_t)b * s.C] = s1[b];
+            }
+          }
+        };
+        ASM_EPILOGUE_CHUNKS(process)
       } else {  // U_DX: thread = batch row, columns = d; split-K partial
         const int row = m0 + lane_row;
         const bool rv = row < s.B;
@@ -633,6 +671,8 @@ cudaError_t umma_configure() {
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(umma_kernel<U_DW>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<U_DW>::SMEM);
   if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(umma_kernel<U_DWOPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<U_DWOPT>::SMEM);
+  if (e != cudaSuccess) return e;
   return cudaFuncSetAttribute(umma_kernel<U_DX>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<U_DX>::SMEM);
 }
 
@@ -672,7 +712,10 @@ void launch_umma_dw(const Step& s, const UmmaMaps& m, const UmmaTuning& tu, int 
   g.nt = (s.D + BN - 1) / BN;
   g.kb_total = (s.B + BK - 1) / BK;
   g.kb_per = g.kb_total;
-  umma_kernel<U_DW><<<min(g.mt * g.nt, num_sms), NUM_THREADS, Geo<U_DW>::SMEM, st>>>(m.g_mn, m.xb_mn, m.wb_box, s, g);
+  if (s.opt.kind != 0)
+    umma_kernel<U_DWOPT><<<min(g.mt * g.nt, num_sms), NUM_THREADS, Geo<U_DWOPT>::SMEM, st>>>(m.g_mn, m.xb_mn, m.wb_box, s, g);
+  else
+    umma_kernel<U_DW><<<min(g.mt * g.nt, num_sms), NUM_THREADS, Geo<U_DW>::SMEM, st>>>(m.g_mn, m.xb_mn, m.wb_box, s, g);
 }
 
 void launch_umma_dx(const Step& s, const UmmaMaps& m, const UmmaTuning& tu, int num_sms,

@@ -121,6 +121,42 @@ def release_handles() -> None:
     _HANDLES.clear()
 
 
+# --------------------------------------------------------------------------------------
+# fused classifier optimizer (the head's share of data_parallel.py:186-196)
+# --------------------------------------------------------------------------------------
+class FusedOptimizer:
+    """Momentum(0.9) / Adam(beta1=0.5, beta2=0.999) update of the classifier weights, with the
+    L2 weight-decay gradient (nets/sphere.py:88, train.py:82 wd=5e-4), executed inside the dW
+    kernel's epilogue: W is updated in place and dW is never written to HBM.
+
+        opt = FusedOptimizer("Momentum", lr=0.1)           # or "Adam"
+        loss, _, dX, _ = asoftmax_head(X, y, C, 4, lam, weights=W, optimizer=opt)   # W updated
+    """
+
+    def __init__(self, kind: str = "Momentum", lr: float = 0.1, momentum: float = 0.9, beta1: float = 0.5,
+                 beta2: float = 0.999, epsilon: float = 1e-8, weight_decay: float = 5e-4):
+        self.kind = {"momentum": _lib.OPT_MOMENTUM, "adam": _lib.OPT_ADAM}[kind.lower()]
+        self.lr, self.momentum, self.beta1, self.beta2 = lr, momentum, beta1, beta2
+        self.epsilon, self.weight_decay = epsilon, weight_decay
+        self.step = 0
+        self.state0 = None
+        self.state1 = None
+
+    def _arm(self, h, weights: torch.Tensor):
+        if self.state0 is None or self.state0.shape != weights.shape:
+            self.state0 = torch.zeros_like(weights)
+            self.state1 = torch.zeros_like(weights) if self.kind == _lib.OPT_ADAM else None
+        self.step += 1
+        o = _lib.AsmOptimizer(self.kind, self.lr, self.momentum, self.beta1, self.beta2, self.epsilon,
+                              self.weight_decay, self.step)
+        _lib.check(h.lib.asm_set_optimizer(h.ptr, C.byref(o), self.state0.data_ptr(),
+                                           self.state1.data_ptr() if self.state1 is not None else None), h.ptr)
+
+    @staticmethod
+    def _disarm(h):
+        h.lib.asm_set_optimizer(h.ptr, None, None, None)
+
+
 def _check_inputs(embeddings, labels, weights, num_classes):
     if not (embeddings.is_cuda and labels.is_cuda and weights.is_cuda):
         raise RuntimeError("embeddings, labels and weights must be CUDA tensors (no CPU fallback)")
@@ -139,7 +175,8 @@ def _check_inputs(embeddings, labels, weights, num_classes):
 def asoftmax_head(embeddings: torch.Tensor, labels: torch.Tensor, num_classes: int, m: int = 4,
                   lambda_state=None, *, weights: torch.Tensor, mode: str = "bf16",
                   return_logits: bool = False, compute_grads: bool = True,
-                  check_labels: bool = False, _handle_tag=None
+                  check_labels: bool = False, optimizer: Optional["FusedOptimizer"] = None,
+                  _handle_tag=None
                   ) -> Tuple[torch.Tensor, Optional[torch.Tensor], Optional[torch.Tensor], Optional[torch.Tensor]]:
     """A-softmax head forward + backward on one GPU that owns every class.
 
@@ -149,10 +186,14 @@ def asoftmax_head(embeddings: torch.Tensor, labels: torch.Tensor, num_classes: i
     batch-mean softmax cross-entropy over the margin logits (nets/sphere.py:109), logits are
     the margin-modified f (only when return_logits: the benchmark path never writes the
     [B, C] matrix to HBM), dX / dW are d(loss)/d(embeddings, weights).
+    With `optimizer` (a FusedOptimizer) the classifier update is fused into the dW kernel:
+    `weights` is updated IN PLACE and the returned dW is None.
     Asynchronous on the current CUDA stream.
     """
     _check_inputs(embeddings, labels, weights, num_classes)
     X = embeddings.contiguous()
+    if optimizer is not None and not weights.is_contiguous():
+        raise ValueError("a fused optimizer updates `weights` in place: it must be contiguous")
     W = weights.contiguous()
     y = labels.contiguous()
     B, D = X.shape
@@ -165,11 +206,17 @@ def asoftmax_head(embeddings: torch.Tensor, labels: torch.Tensor, num_classes: i
     with torch.cuda.device(X.device):
         if compute_grads:
             dX = torch.empty_like(X)
-            dW = torch.empty_like(W)
-            rc = h.lib.asm_forward_backward(
-                h.ptr, X.data_ptr(), B, y.data_ptr(), y.element_size(), W.data_ptr(), lam,
-                loss.data_ptr(), logits.data_ptr() if logits is not None else None,
-                dX.data_ptr(), dW.data_ptr(), stream)
+            dW = torch.empty_like(W) if optimizer is None else None
+            if optimizer is not None:
+                optimizer._arm(h, W)
+            try:
+                rc = h.lib.asm_forward_backward(
+                    h.ptr, X.data_ptr(), B, y.data_ptr(), y.element_size(), W.data_ptr(), lam,
+                    loss.data_ptr(), logits.data_ptr() if logits is not None else None,
+                    dX.data_ptr(), dW.data_ptr() if dW is not None else None, stream)
+            finally:
+                if optimizer is not None:
+                    optimizer._disarm(h)
         else:
             dX = dW = None
             rc = h.lib.asm_forward(
