@@ -146,6 +146,22 @@ typedef struct {
 } asm_optimizer;
 int asm_set_optimizer(asm_head* h, const asm_optimizer* opt, float* state0, float* state1);
 
+/*
+ * Center loss (loss.py:29-45), sharded by class like W.
+ *   loss      = mean(square(features - centers[labels]))   over B*D, with the PRE-update centers
+ *   centers   = scatter_sub(centers, labels, (1 - alpha) * (centers[labels] - features))
+ *               (duplicate labels accumulate), updated in place
+ *   dX_accum += weight * 2 (features - centers[labels]) / (B*D)       (optional, may be NULL)
+ * A shard only touches rows whose label lies in [class_offset, class_offset + C_local); its
+ * loss_out is that shard's partial sum / (B*D) (sum the shards' values).  `scratch` is a
+ * caller-owned device buffer of (B + 1) floats whose last word is zero on first use.
+ * Deterministic (no float atomics).  Stateless: no handle needed.
+ */
+int asm_center_loss(const float* X, int32_t B, int32_t D, const void* labels, int32_t label_bytes,
+                    float* centers, int32_t C_local, int32_t class_offset, float alpha,
+                    float weight, float* loss_out, float* dX_accum_or_null, float* scratch,
+                    void* cuda_stream);
+
 /* CUDA-graph support.  Kernel arguments are frozen when a step is captured into a graph, so
  * lambda (which anneals per step) can instead be read from a caller-owned DEVICE float:
  * once set (non-NULL) it overrides the by-value `lambda` argument of every step call; NULL

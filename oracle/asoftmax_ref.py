@@ -223,3 +223,23 @@ def optimizer_step(W, dW, state0, state1, kind="momentum", lr=0.1, momentum=0.9,
     v = beta2 * np.asarray(state1, dtype=np.float64) + (1 - beta2) * g * g
     lr_t = lr * math.sqrt(1 - beta2 ** step) / (1 - beta1 ** step)
     return W - lr_t * m / (np.sqrt(v) + epsilon), m, v
+
+
+# --------------------------------------------------------------------------------------
+# center loss (loss.py:29-45)
+# --------------------------------------------------------------------------------------
+def center_loss(features, labels, centers, alpha=0.99, weight=1.0):
+    """Restates loss.py:29-45: centers_batch = gather(centers, labels); diffs = (1-alpha) *
+    (centers_batch - features); centers = scatter_sub(centers, labels, diffs) (duplicates
+    accumulate); loss = mean(square(features - centers_batch)) with the PRE-update centers.
+    Returns (loss, centers_new, d(weight*loss)/d(features))."""
+    X = np.asarray(features, dtype=np.float64)
+    y = np.asarray(labels).astype(np.int64)
+    Cn = np.asarray(centers, dtype=np.float64)
+    cb = Cn[y]
+    diffs = (1.0 - alpha) * (cb - X)
+    new = Cn.copy()
+    np.subtract.at(new, y, diffs)
+    loss = float(np.mean((X - cb) ** 2))
+    grad = weight * 2.0 * (X - cb) / X.size
+    return loss, new, grad

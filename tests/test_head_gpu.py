@@ -308,3 +308,31 @@ def test_fused_optimizer_matches_unfused_update(kind, mode):
     # the plain path is unaffected afterwards (optimizer disarmed): dW is returned again
     _, _, _, dW2 = asoftmax_head(X, y, Cn, 4, 5.0, weights=W_f, mode=mode)
     assert dW2 is not None
+
+
+def test_center_loss_gpu_matches_oracle_including_duplicates_and_shards():
+    """§8f-2: center loss (loss.py:29-45) on the GPU, whole and class-sharded."""
+    from tf_face_toolbox_b200.center import center_loss
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(5)
+    B, D, Cn = 300, 512, 40                       # many duplicate labels
+    X = torch.randn(B, D, generator=g)
+    y = torch.randint(0, Cn, (B,), generator=g).to(torch.int32)
+    cen = torch.randn(Cn, D, generator=g) * 0.1
+    loss_r, new_r, grad_r = ref.center_loss(X.numpy(), y.numpy(), cen.numpy(), alpha=0.95, weight=0.7)
+    c_dev = cen.clone().to(dev)
+    loss, grad = center_loss(X.to(dev), y.to(dev), c_dev, alpha=0.95, weight=0.7)
+    torch.cuda.synchronize()
+    assert float(loss) == pytest.approx(loss_r, rel=1e-5)
+    np.testing.assert_allclose(grad.cpu().numpy(), grad_r, rtol=1e-4, atol=1e-9)
+    np.testing.assert_allclose(c_dev.cpu().numpy(), new_r, rtol=1e-4, atol=1e-6)
+    # two class shards: partial losses add up, gradients / updates are disjoint
+    lo = 17
+    cA, cB = cen[:lo].clone().to(dev), cen[lo:].clone().to(dev)
+    acc = torch.zeros(B, D, device=dev)
+    lA, _ = center_loss(X.to(dev), y.to(dev), cA, 0.95, 0.7, class_offset=0, grad_accum=acc)
+    lB, _ = center_loss(X.to(dev), y.to(dev), cB, 0.95, 0.7, class_offset=lo, grad_accum=acc)
+    torch.cuda.synchronize()
+    assert float(lA) + float(lB) == pytest.approx(loss_r, rel=1e-5)
+    np.testing.assert_allclose(acc.cpu().numpy(), grad_r, rtol=1e-4, atol=1e-9)
+    np.testing.assert_allclose(torch.cat([cA, cB]).cpu().numpy(), new_r, rtol=1e-4, atol=1e-6)
