@@ -162,6 +162,30 @@ int asm_center_loss(const float* X, int32_t B, int32_t D, const void* labels, in
                     float weight, float* loss_out, float* dX_accum_or_null, float* scratch,
                     void* cuda_stream);
 
+/*
+ * NVLink peer-memory transport of the class-sharded step: the whole step of one rank --
+ * gather of X / labels, statistics exchange, dX reduce-scatter included -- in ONE call, with
+ * no NCCL launch: the head's kernels read the peers' symmetric buffers over NVLink (P2P loads)
+ * and synchronise with release/acquire flags.  Replaces asm_forward_partial + host
+ * collectives + asm_backward_partial (and with them nccl.all_sum, data_parallel.py:175-181).
+ *   asm_p2p_bytes   bytes of peer-mapped ("symmetric") device memory every rank must provide
+ *                   for cfg (B_max = largest GLOBAL batch; cfg->world ranks)
+ *   asm_p2p_attach  peer_bases[world]: the device address, valid on THIS rank, of every rank's
+ *                   block (own rank included).  The blocks must be zero-filled before the
+ *                   first step of any rank (e.g. zero + barrier on the host).
+ *   asm_step_p2p    X_local [b_local, D] / labels_local [b_local]: this rank's rows (every
+ *                   rank passes the same b_local; global batch = b_local * world);
+ *                   W / dW: this shard's [D, C_local]; loss_out: global mean loss;
+ *                   dX_local [b_local, D]: the complete gradient of this rank's rows.
+ * Asynchronous on cuda_stream and capturable into a CUDA graph.  A peer that never arrives
+ * makes the waiting kernel trap after ~2 s (reported as a CUDA error) instead of hanging.
+ */
+size_t asm_p2p_bytes(const asm_config* cfg);
+int asm_p2p_attach(asm_head* h, void* const* peer_bases);
+int asm_step_p2p(asm_head* h, const float* X_local, int32_t b_local, const void* labels_local,
+                 int32_t label_bytes, const float* W, float lambda, float* loss_out,
+                 float* dX_local, float* dW, void* cuda_stream);
+
 /* CUDA-graph support.  Kernel arguments are frozen when a step is captured into a graph, so
  * lambda (which anneals per step) can instead be read from a caller-owned DEVICE float:
  * once set (non-NULL) it overrides the by-value `lambda` argument of every step call; NULL

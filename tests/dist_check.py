@@ -27,12 +27,18 @@ def main():
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
     ok = True
-    for (B, D, C, mode, tol) in [(64, 128, 5000, "fp32", 1e-5), (512, 512, 10572, "bf16", 2e-3), (512, 512, 85742, "bf16", 2e-3)]:
+    transports = sys.argv[1:] or ["nccl", "nvlink"]
+    cases = [(64, 128, 5000, "fp32", 1e-5), (512, 512, 10572, "bf16", 2e-3), (512, 512, 85742, "bf16", 2e-3)]
+    for transport in transports:
+      for (B, D, C, mode, tol) in cases:
         inp = make_inputs(B, D, C, seed=77)
-        head = ShardedASoftmaxHead(D, C, m=4, mode=mode, device=dev, weights_full=inp.W)
+        head = ShardedASoftmaxHead(D, C, m=4, mode=mode, device=dev, weights_full=inp.W,
+                                   transport=transport, batch_global=B)
         b = B // world
-        loss, dX, dW = head.step(inp.X[rank * b:(rank + 1) * b].to(dev), inp.y[rank * b:(rank + 1) * b].to(dev), 5.0)
+        for it in range(3):          # several steps: exercises the parity double-buffering
+            loss, dX, dW = head.step(inp.X[rank * b:(rank + 1) * b].to(dev), inp.y[rank * b:(rank + 1) * b].to(dev), 5.0)
         torch.cuda.synchronize()
+        mode = f"{transport}/{mode}"
         r = ref.asoftmax_head(inp.X.numpy(), inp.W.numpy(), inp.y.numpy(), 4, 5.0)
         rel = abs(float(loss) - r.loss) / r.loss
         cx = cos(dX.cpu().numpy(), r.dX[rank * b:(rank + 1) * b])

@@ -21,7 +21,7 @@ def lib():
 
 def test_every_header_symbol_is_exported(lib):
     hdr = open(os.path.join(ROOT, "include", "asoftmax_b200.h")).read()
-    declared = set(re.findall(r"\b(asm_[a-z_]+)\s*\(", hdr))
+    declared = set(re.findall(r"\b(asm_[a-z0-9_]+)\s*\(", hdr))
     assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
     for name in declared:
         assert hasattr(lib, name)

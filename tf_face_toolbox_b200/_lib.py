@@ -65,6 +65,9 @@ SYMBOLS = {
     "asm_set_optimizer": (C.c_int, [_P, C.POINTER(AsmOptimizer), _P, _P]),
     "asm_center_loss": (C.c_int, [_P, C.c_int32, C.c_int32, _P, C.c_int32, _P, C.c_int32, C.c_int32,
                                   C.c_float, C.c_float, _P, _P, _P, _P]),
+    "asm_p2p_bytes": (C.c_size_t, [C.POINTER(AsmConfig)]),
+    "asm_p2p_attach": (C.c_int, [_P, C.POINTER(C.c_void_p)]),
+    "asm_step_p2p": (C.c_int, [_P, _P, C.c_int32, _P, C.c_int32, _P, C.c_float, _P, _P, _P, _P]),
     "asm_set_lambda_device": (C.c_int, [_P, _P]),
     "asm_set_profiling": (C.c_int, [_P, C.c_int]),
     "asm_get_profile": (C.c_int, [_P, C.c_int32, _P, _P]),

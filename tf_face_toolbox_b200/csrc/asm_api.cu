@@ -32,6 +32,12 @@ struct asm_head {
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool overlap = true;           // ASM_NO_OVERLAP=1 disables
+  // NVLink peer-memory transport (asm_p2p_attach / asm_step_p2p)
+  P2P p2p{};
+  bool p2p_ready = false;
+  float* Xg = nullptr;           // [B_max, D] gathered embeddings
+  int* yg = nullptr;             // [B_max]    gathered labels
+  float* stats_all = nullptr;    // [world, 3, B_max]
   size_t l2_persist_bytes = 0;   // ASM_L2_PERSIST_MB: pin the bf16 weight copy in L2
   cudaStream_t l2_stream = nullptr;
   bool l2_set = false;
@@ -52,7 +58,7 @@ size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct Layout {
   size_t ylocal, flags, n, inv_n, inv_c, tgt_s, tgt_f, part, stats_local, lse, negoff, gtarget, rcoef, rowloss, counter,
-      q_part, G, dx_part, Xb, Wb, total;
+      q_part, G, dx_part, Xb, Wb, Xg, yg, stats_all, step_dev, total;
   int Cp, NT, MT;
   size_t dx_capacity;
 };
@@ -109,6 +115,12 @@ Layout make_layout(const asm_config& c, int num_sms) {
   if (c.mode == ASM_MODE_BF16) {
     L.Xb = take(B * D * 2);
     L.Wb = take(D * (size_t)L.Cp * 2);
+  }
+  if (c.world > 1) {
+    L.Xg = take(B * D * 4);
+    L.yg = take(B * 4);
+    L.stats_all = take((size_t)c.world * 3 * B * 4);
+    L.step_dev = take(256);
   }
   L.total = off;
   return L;
@@ -363,6 +375,12 @@ int asm_create(asm_head** out, const asm_config* cfg) {
     s.Xb = (__nv_bfloat16*)(w + L.Xb);
     s.Wb = (__nv_bfloat16*)(w + L.Wb);
   }
+  if (cfg->world > 1) {
+    h->Xg = (float*)(w + L.Xg);
+    h->yg = (int*)(w + L.yg);
+    h->stats_all = (float*)(w + L.stats_all);
+    h->p2p.step_dev = (unsigned*)(w + L.step_dev);
+  }
   h->Cp = L.Cp;
   *out = h;
   return ASM_OK;
@@ -431,6 +449,94 @@ int asm_forward(asm_head* h, const float* X, int32_t B, const void* labels, int3
   if (rc != ASM_OK) return rc;
   if (!loss_out) return fail(h, ASM_ERR_INVALID_ARG, "loss_out is NULL%s", "");
   return run_backward(h, nullptr, 1, loss_out, nullptr, nullptr, false, stream);
+}
+
+namespace {
+struct P2PLayout { size_t off_x, off_y, off_st, off_dx, off_fl, total; int b_max; };
+P2PLayout p2p_layout(const asm_config& c) {
+  P2PLayout L{};
+  const size_t B = c.B_max, D = c.D;
+  L.b_max = (int)((B + c.world - 1) / c.world);
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+  L.off_x = take(2 * (size_t)L.b_max * D * 4);
+  L.off_y = take(2 * (size_t)L.b_max * 4);
+  L.off_st = take(2 * 3 * B * 4);
+  L.off_dx = take(2 * B * D * 4);
+  L.off_fl = take(3 * kFlagStride * 4);
+  L.total = off;
+  return L;
+}
+}  // namespace
+
+size_t asm_p2p_bytes(const asm_config* cfg) {
+  if (!valid_cfg(cfg) || cfg->world < 2 || cfg->world > kMaxPeers) return 0;
+  return p2p_layout(*cfg).total;
+}
+
+int asm_p2p_attach(asm_head* h, void* const* peer_bases) {
+  if (!h || !peer_bases) return ASM_ERR_INVALID_ARG;
+  if (h->cfg.world < 2 || h->cfg.world > kMaxPeers)
+    return fail(h, ASM_ERR_INVALID_ARG, "asm_p2p_attach needs 2..8 ranks%s", "");
+  const P2PLayout L = p2p_layout(h->cfg);
+  P2P& p = h->p2p;
+  p.rank = h->cfg.rank;
+  p.world = h->cfg.world;
+  p.b_max = L.b_max;
+  p.B_max = h->cfg.B_max;
+  p.D = h->cfg.D;
+  p.off_x = L.off_x; p.off_y = L.off_y; p.off_st = L.off_st; p.off_dx = L.off_dx; p.off_fl = L.off_fl;
+  for (int r = 0; r < p.world; ++r) {
+    if (!peer_bases[r]) return fail(h, ASM_ERR_INVALID_ARG, "peer base is NULL%s", "");
+    p.base[r] = (char*)peer_bases[r];
+  }
+  h->p2p_ready = true;
+  return ASM_OK;
+}
+
+int asm_step_p2p(asm_head* h, const float* X_local, int32_t b_local, const void* labels_local,
+                 int32_t label_bytes, const float* W, float lambda, float* loss_out,
+                 float* dX_local, float* dW, void* cuda_stream) {
+  if (!h) return ASM_ERR_INVALID_ARG;
+  if (!h->p2p_ready) return fail(h, ASM_ERR_INVALID_ARG, "asm_step_p2p before asm_p2p_attach%s", "");
+  if (!X_local || !labels_local || !W || !loss_out || !dX_local || (!dW && h->st.opt.kind == 0))
+    return fail(h, ASM_ERR_INVALID_ARG, "null pointer%s", "");
+  if (label_bytes != 4 && label_bytes != 8)
+    return fail(h, ASM_ERR_INVALID_ARG, "label_bytes must be 4 or 8%s", "");
+  P2P& p = h->p2p;
+  if (b_local <= 0 || b_local > p.b_max || (long long)b_local * p.world > h->cfg.B_max)
+    return fail(h, ASM_ERR_INVALID_ARG, "b_local out of range%s", "");
+  cudaStream_t stream = (cudaStream_t)cuda_stream;
+  p.b_local = b_local;
+  const int B = b_local * p.world;
+  Step& s = h->st;
+  // phase 0: publish my rows, gather everybody's
+  launch_p2p_pack(p, X_local, labels_local, label_bytes, s.D, stream);
+  launch_p2p_signal(p, 0, 1, stream);
+  launch_p2p_gather_x(p, h->Xg, h->yg, s.D, stream);
+  // forward on the gathered batch; this shard's statistics go to its symmetric block
+  float* ws_stats = s.stats_local;
+  s.par_step = p.step_dev;
+  s.stats_par_stride = (size_t)3 * p.B_max;
+  s.dx_par_stride = (size_t)p.B_max * s.D;
+  s.stats_local = p.st(p.rank, 0);
+  int rc = run_forward(h, h->Xg, B, h->yg, 4, W, lambda, nullptr, true, stream);
+  if (rc == ASM_OK) {
+    launch_p2p_signal(p, 1, 0, stream);
+    launch_p2p_gather_stats(p, h->stats_all, B, stream);
+    // backward; my dX contribution for all rows goes to the symmetric block, then every rank
+    // sums its own rows over the shards
+    rc = run_backward(h, h->stats_all, p.world, loss_out, p.dx(p.rank, 0), dW, true, stream);
+  }
+  if (rc == ASM_OK) {
+    launch_p2p_signal(p, 2, 0, stream);
+    launch_p2p_reduce_dx(p, dX_local, s.D, stream);
+    h->launches += 7;
+    rc = check_launch(h, "p2p launch");
+  }
+  s.stats_local = ws_stats;
+  s.par_step = nullptr;
+  return rc;
 }
 
 int asm_set_optimizer(asm_head* h, const asm_optimizer* opt, float* state0, float* state1) {

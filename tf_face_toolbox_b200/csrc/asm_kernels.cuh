@@ -34,6 +34,38 @@ __host__ __device__ inline void opt_apply(const OptParams& o, float grad, float&
   }
 }
 
+// NVLink peer-memory transport of the class-sharded step (asm_p2p.cu)
+constexpr int kMaxPeers = 8;
+constexpr int kFlagStride = 16;        // flag words per phase
+struct P2P {
+  int rank, world, b_local, b_max, B_max, D;
+  unsigned* step_dev;                  // device step counter of this rank
+  char* base[kMaxPeers];               // every rank's symmetric block (own included)
+  size_t off_x, off_y, off_st, off_dx, off_fl;
+  __host__ __device__ float* x(int r, int par) const {
+    return reinterpret_cast<float*>(base[r] + off_x) + (size_t)par * b_max * D;
+  }
+  __host__ __device__ int* y(int r, int par) const {
+    return reinterpret_cast<int*>(base[r] + off_y) + (size_t)par * b_max;
+  }
+  __host__ __device__ float* st(int r, int par) const {
+    return reinterpret_cast<float*>(base[r] + off_st) + (size_t)par * 3 * B_max;
+  }
+  __host__ __device__ float* dx(int r, int par) const {
+    return reinterpret_cast<float*>(base[r] + off_dx) + (size_t)par * B_max * D;
+  }
+  __host__ __device__ unsigned* flags_of(int r) const {
+    return reinterpret_cast<unsigned*>(base[r] + off_fl);
+  }
+  __host__ __device__ unsigned* flags_local() const { return flags_of(rank); }
+};
+void launch_p2p_pack(const P2P& p, const float* X, const void* labels, int label_bytes, int D,
+                     cudaStream_t st);
+void launch_p2p_signal(const P2P& p, int phase, int bump, cudaStream_t st);
+void launch_p2p_gather_x(const P2P& p, float* Xg, int* yg, int D, cudaStream_t st);
+void launch_p2p_gather_stats(const P2P& p, float* stats_all, int B, cudaStream_t st);
+void launch_p2p_reduce_dx(const P2P& p, float* dX_local, int D, cudaStream_t st);
+
 constexpr int kRowTileHost = 128;   // == asmh::kRowTile (asm_common.cuh)
 
 struct Step {
@@ -76,6 +108,10 @@ struct Step {
   float* Wmut;               // [D, C]  W, updated in place when opt.kind != 0
   float* opt_s0;             // [D, C]  momentum accumulator / adam m
   float* opt_s1;             // [D, C]  adam v
+  // P2P transport: outputs that live in the parity-double-buffered symmetric block are
+  // addressed as base + (*par_step & 1) * stride on the device (CUDA-graph friendly)
+  const unsigned* par_step;
+  size_t stats_par_stride, dx_par_stride;   // in floats
 };
 
 // prep: column norms of W (+ bf16 copy), row norms of X (+ bf16 copy), label localisation

@@ -148,9 +148,10 @@ __global__ void __launch_bounds__(256) combine_local_kernel(Step s) {
     ms_combine(m, z, m2, z2);
   }
   if (lane == 0) {
-    s.stats_local[row] = m;
-    s.stats_local[s.B + row] = z;
-    s.stats_local[2 * s.B + row] = s.ylocal[row] >= 0 ? s.tgt_f[row] : 0.f;
+    float* st = s.stats_local + (s.par_step ? (size_t)(*s.par_step & 1) * s.stats_par_stride : 0);
+    st[row] = m;
+    st[s.B + row] = z;
+    st[2 * s.B + row] = s.ylocal[row] >= 0 ? s.tgt_f[row] : 0.f;
   }
 }
 
@@ -282,7 +283,8 @@ __global__ void __launch_bounds__(256) dx_finish_kernel(Step s) {
       const float4 v = __ldcg(p + (size_t)z * stride4);
       a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
     }
-    reinterpret_cast<float4*>(s.dX)[i] = a;
+    float* dxo = s.dX + (s.par_step ? (size_t)(*s.par_step & 1) * s.dx_par_stride : 0);
+    reinterpret_cast<float4*>(dxo)[i] = a;
   }
 }
 

@@ -78,7 +78,8 @@ class ShardedASoftmaxHead:
 
     def __init__(self, num_features: int, num_classes: int, m: int = 4, mode: str = "bf16",
                  device="cuda", group=None, lambda_state: Optional[LambdaState] = None,
-                 weights_full: Optional[torch.Tensor] = None, seed: int = 0, shard_compute=None):
+                 weights_full: Optional[torch.Tensor] = None, seed: int = 0, shard_compute=None,
+                 transport: str = "nccl", batch_global: Optional[int] = None):
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -96,6 +97,16 @@ class ShardedASoftmaxHead:
         self.lambda_state = lambda_state if lambda_state is not None else LambdaState()
         self.compute = shard_compute if shard_compute is not None else _CudaShard(
             num_features, num_classes, self.lo, self.hi, m, mode, self.rank, self.world, self.device)
+        # transport "nvlink": no NCCL in the step -- the library's kernels read the peers'
+        # symmetric buffers over NVLink (asm_step_p2p).  Needs the global batch up front.
+        self.transport = transport
+        self._p2p = None
+        if transport == "nvlink" and self.world > 1:
+            if batch_global is None:
+                raise ValueError("transport='nvlink' needs batch_global (rows of the gathered batch)")
+            self._p2p = self._attach_p2p(batch_global)
+        elif transport not in ("nccl", "nvlink"):
+            raise ValueError("transport must be 'nccl' or 'nvlink'")
 
     # ---- collectives (torch.distributed plumbing) ------------------------------------
     def _all_gather(self, t: torch.Tensor) -> torch.Tensor:
@@ -117,12 +128,48 @@ class ShardedASoftmaxHead:
             dist.reduce_scatter_tensor(out, full, group=self.group)
         return out
 
+    # ---- NVLink peer-memory transport ------------------------------------------------------
+    def _attach_p2p(self, batch_global: int, tag="p2p"):
+        import torch.distributed._symmetric_memory as symm_mem
+        D, C_total, C_local, lo, m, mode, rank, world = self.compute.args
+        h = get_handle(self.device, D, C_total, C_local, lo, batch_global, m, mode, rank, world,
+                       tag=(tag, id(self)))
+        nbytes = int(h.lib.asm_p2p_bytes(C.byref(h.cfg)))
+        if nbytes == 0:
+            raise RuntimeError("asm_p2p_bytes: unsupported configuration (2..8 ranks)")
+        buf = symm_mem.empty(nbytes, dtype=torch.uint8, device=self.device)
+        buf.zero_()
+        hdl = symm_mem.rendezvous(buf, self.group if self.group is not None else dist.group.WORLD)
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)            # every block is zero before anyone signals
+        ptrs = (C.c_void_p * world)(*[int(p) for p in hdl.buffer_ptrs])
+        _lib.check(h.lib.asm_p2p_attach(h.ptr, ptrs), h.ptr)
+        return dict(handle=h, buf=buf, hdl=hdl, batch=batch_global)
+
+    def _step_p2p(self, embeddings_local, labels_local, lam, p2p=None):
+        p2p = p2p or self._p2p
+        h = p2p["handle"]
+        X = embeddings_local.contiguous()
+        y = labels_local.contiguous()
+        b = X.shape[0]
+        loss = torch.empty(1, device=X.device, dtype=torch.float32)
+        dX = torch.empty_like(X)
+        dW = torch.empty_like(self.weights)
+        stream = C.c_void_p(torch.cuda.current_stream(X.device).cuda_stream)
+        with torch.cuda.device(X.device):
+            _lib.check(h.lib.asm_step_p2p(h.ptr, X.data_ptr(), b, y.data_ptr(), y.element_size(),
+                                          self.weights.data_ptr(), lam, loss.data_ptr(), dX.data_ptr(),
+                                          dW.data_ptr(), stream), h.ptr)
+        return loss[0], dX, dW
+
     # ---- one training step of the head -------------------------------------------------
     def step(self, embeddings_local: torch.Tensor, labels_local: torch.Tensor, lambda_state=None):
         """embeddings_local [B/G, D], labels_local [B/G] (this rank's data-parallel slice,
         data_parallel.py:206-207).  Returns (loss, dX_local [B/G, D], dW_local [D, C_local]);
         loss is the global-batch mean and identical on every rank."""
         lam = _as_lambda(lambda_state) if lambda_state is not None else self.lambda_state.step()
+        if self._p2p is not None:
+            return self._step_p2p(embeddings_local, labels_local, lam)
         b = embeddings_local.shape[0]
         X = self._all_gather(embeddings_local).reshape(-1, self.D)
         y = self._all_gather(labels_local).reshape(-1)
