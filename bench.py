@@ -211,32 +211,66 @@ def run_ours(args, cfg):
 
         def step():
             return head.step(Xd, yd, LAMBDA)
+        # the same step with the collectives done by the head's own kernels over NVLink peer
+        # memory (no NCCL launch in the step)
+        head_nv = None
+        if not args.no_nvlink:
+            try:
+                head_nv = ShardedASoftmaxHead(D, Cn, m=M_MARGIN, mode=mode, device=dev, weights_full=inp.W,
+                                              transport="nvlink", batch_global=B)
+                head_nv.step(Xd, yd, LAMBDA)
+                torch.cuda.synchronize()
+            except Exception as e:      # pragma: no cover
+                print(f"bench: nvlink transport unavailable ({type(e).__name__}: {e})", file=sys.stderr)
+                head_nv = None
+            okt = torch.tensor([1 if head_nv is not None else 0], device=dev)
+            dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+            if int(okt.item()) == 0:
+                head_nv = None
 
     # CUDA-graph replay of the same step (one launch instead of 7 kernels / 3 collectives):
     # the public GraphedASoftmaxStep / ShardedASoftmaxHead.capture API.  Falls back to the
     # eager call if capture is not possible.
-    graphed = None
-    if not args.no_graph:
-        try:
-            if world == 1:
-                gstep = GraphedASoftmaxStep(Wd, batch_size=B, m=M_MARGIN, mode=mode)
-                graphed = lambda X, y: gstep(X, y, LAMBDA)
-            else:
-                head.capture(b_local)
-                graphed = lambda X, y: head.step_graphed(X, y, LAMBDA)
-            graphed(Xd, yd)
-            torch.cuda.synchronize()
-        except Exception as e:      # pragma: no cover
-            print(f"bench: CUDA-graph capture unavailable ({type(e).__name__}: {e}); eager path", file=sys.stderr)
-            graphed = None
-    if world > 1:
-        ok = torch.tensor([1 if graphed is not None else 0], device=dev)
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-        if int(ok.item()) == 0:
-            graphed = None
+    def try_capture(make):
+        g = None
+        if not args.no_graph:
+            try:
+                g = make()
+                g(Xd, yd)
+                torch.cuda.synchronize()
+            except Exception as e:      # pragma: no cover
+                print(f"bench: CUDA-graph capture unavailable ({type(e).__name__}: {e})", file=sys.stderr)
+                g = None
+        if world > 1:
+            ok = torch.tensor([1 if g is not None else 0], device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok.item()) == 0:
+                g = None
+        return g
+
+    def make_graph_main():
+        if world == 1:
+            gstep = GraphedASoftmaxStep(Wd, batch_size=B, m=M_MARGIN, mode=mode)
+            return lambda X, y: gstep(X, y, LAMBDA)
+        head.capture(b_local)
+        return lambda X, y: head.step_graphed(X, y, LAMBDA)
+
+    def make_graph_nv():
+        head_nv.capture(b_local)
+        return lambda X, y: head_nv.step_graphed(X, y, LAMBDA)
+    graphed = try_capture(make_graph_main)
+    # each path: name -> (device-resident step, host-input step)
     paths = {"eager": step}
+    host_paths = {}
     if graphed is not None:
         paths["graph"] = lambda: graphed(Xd, yd)
+        host_paths["graph"] = graphed
+    if world > 1 and head_nv is not None:
+        paths["nvlink"] = lambda: head_nv.step(Xd, yd, LAMBDA)
+        graphed_nv = try_capture(make_graph_nv)
+        if graphed_nv is not None:
+            paths["nvlink_graph"] = lambda: graphed_nv(Xd, yd)
+            host_paths["nvlink_graph"] = graphed_nv
 
     def barrier():
         if world > 1:
@@ -318,21 +352,27 @@ def run_ours(args, cfg):
     yh = (inp.y if world == 1 else inp.y[rank * b_local:(rank + 1) * b_local]).contiguous().pin_memory()
     loss_h = torch.empty(1, dtype=torch.float32).pin_memory()
 
-    def e2e_eager():
-        Xd.copy_(Xh, non_blocking=True)
-        yd.copy_(yh, non_blocking=True)
-        out = step()
-        loss_h.copy_(out[0].reshape(1), non_blocking=False)      # D2H read of the result (syncs)
-        return out
+    def make_e2e(name):
+        if name in host_paths:                # graph steps copy their (host) inputs themselves
+            g = host_paths[name]
 
-    def e2e_graph():
-        out = graphed(Xh, yh)                 # H2D copies of X / labels happen inside the call
-        loss_h.copy_(out[0].reshape(1), non_blocking=False)
-        return out
+            def fn():
+                out = g(Xh, yh)
+                loss_h.copy_(out[0].reshape(1), non_blocking=False)   # D2H read of the result (syncs)
+                return out
+        else:
+            dev_step = paths[name]
+
+            def fn():
+                Xd.copy_(Xh, non_blocking=True)
+                yd.copy_(yh, non_blocking=True)
+                out = dev_step()
+                loss_h.copy_(out[0].reshape(1), non_blocking=False)
+                return out
+        return fn
     e2e_ms = {}
-    for name, fn in (("eager", e2e_eager), ("graph", e2e_graph if graphed is not None else None)):
-        if fn is None:
-            continue
+    for name in paths:
+        fn = make_e2e(name)
         for _ in range(3):
             fn()
         e2e_ms[name] = timed(fn, K) / K - flush_ms
@@ -432,9 +472,12 @@ def run_ours(args, cfg):
         bail.start()
         graphed = None
         run_step = None
-        for attr in ("_graph", "_gout"):
-            if hasattr(head, attr):
-                setattr(head, attr, None)
+        paths.clear()
+        host_paths.clear()
+        for hd in (head, head_nv):
+            for attr in ("_graph", "_gout"):
+                if hd is not None and hasattr(hd, attr):
+                    setattr(hd, attr, None)
         torch.cuda.synchronize()
         dist.barrier()
         dist.destroy_process_group()
@@ -453,6 +496,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time the eager per-kernel launches")
     ap.add_argument("--graph", action="store_true", help="(default) also time the CUDA-graph replay of the step")
+    ap.add_argument("--no-nvlink", action="store_true", help="N>1: skip the NVLink peer-memory transport")
     args = ap.parse_args()
     cfg = dict(CONFIGS[args.workload])
     if args.mode is None:

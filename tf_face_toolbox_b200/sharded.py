@@ -189,6 +189,26 @@ class ShardedASoftmaxHead:
         self._gy = torch.zeros(batch_local, device=dev, dtype=labels_dtype)
         self._glam = torch.zeros(1, device=dev, dtype=torch.float32)
         self._glam_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+        if self._p2p is not None:
+            # NVLink transport: a second symmetric block + handle whose kernels read lambda from
+            # the device scalar; the captured graph contains no NCCL node at all
+            p2pg = self._attach_p2p(batch_local * self.world, tag="p2pgraph")
+            hg = p2pg["handle"]
+            _lib.check(hg.lib.asm_set_lambda_device(hg.ptr, self._glam.data_ptr()), hg.ptr)
+            self._p2pg = p2pg
+            cur = torch.cuda.current_stream(dev)
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    self._step_p2p(self._gX, self._gy, 0.0, p2p=p2pg)
+            cur.wait_stream(side)
+            torch.cuda.synchronize(dev)
+            dist.barrier(group=self.group)
+            self._graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph):
+                self._gout = self._step_p2p(self._gX, self._gy, 0.0, p2p=p2pg)
+            return self
         # a dedicated shard-compute object (own handle / workspace) whose kernels read lambda
         # from the device scalar; the eager step() keeps its own by-value handle
         eager_compute = self.compute
