@@ -258,32 +258,43 @@ void launch_combine_fused(const Step& s, cudaStream_t st) {
 // ---------------------------------------------------------------------------------------
 // dx_finish: dX = sum_z dx_part[z] + r_i * x_i   (float4 along D; D % 4 == 0)
 // ---------------------------------------------------------------------------------------
+// KS_T > 0: all KS_T partial loads are issued before the first add (one memory round trip);
+// KS_T == 0: generic loop in batches of four.  Summation order z = 0..KS-1 either way.
+template <int KS_T>
 __global__ void __launch_bounds__(256) dx_finish_kernel(Step s) {
   const size_t total4 = (size_t)s.B * s.D / 4;
   const size_t stride4 = total4;
+  float* dxo = s.dX + (s.par_step ? (size_t)(*s.par_step & 1) * s.dx_par_stride : 0);
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total4;
        i += (size_t)gridDim.x * blockDim.x) {
     const int row = (int)((i * 4) / s.D);
+    const float4* p = reinterpret_cast<const float4*>(s.dx_part) + i;
     const float r = s.rcoef[row];
     const float4 x = __ldg(reinterpret_cast<const float4*>(s.X) + i);
     float4 a = make_float4(r * x.x, r * x.y, r * x.z, r * x.w);
-    const float4* p = reinterpret_cast<const float4*>(s.dx_part) + i;
-    int z = 0;
-    for (; z + 4 <= s.KS; z += 4) {                 // four independent loads in flight
-      const float4 v0 = __ldcg(p + (size_t)(z + 0) * stride4);
-      const float4 v1 = __ldcg(p + (size_t)(z + 1) * stride4);
-      const float4 v2 = __ldcg(p + (size_t)(z + 2) * stride4);
-      const float4 v3 = __ldcg(p + (size_t)(z + 3) * stride4);
-      a.x += v0.x; a.y += v0.y; a.z += v0.z; a.w += v0.w;
-      a.x += v1.x; a.y += v1.y; a.z += v1.z; a.w += v1.w;
-      a.x += v2.x; a.y += v2.y; a.z += v2.z; a.w += v2.w;
-      a.x += v3.x; a.y += v3.y; a.z += v3.z; a.w += v3.w;
+    if (KS_T > 0) {
+      float4 v[KS_T > 0 ? KS_T : 1];
+#pragma unroll
+      for (int z = 0; z < KS_T; ++z) v[z] = __ldcg(p + (size_t)z * stride4);
+#pragma unroll
+      for (int z = 0; z < KS_T; ++z) { a.x += v[z].x; a.y += v[z].y; a.z += v[z].z; a.w += v[z].w; }
+    } else {
+      int z = 0;
+      for (; z + 4 <= s.KS; z += 4) {
+        const float4 v0 = __ldcg(p + (size_t)(z + 0) * stride4);
+        const float4 v1 = __ldcg(p + (size_t)(z + 1) * stride4);
+        const float4 v2 = __ldcg(p + (size_t)(z + 2) * stride4);
+        const float4 v3 = __ldcg(p + (size_t)(z + 3) * stride4);
+        a.x += v0.x; a.y += v0.y; a.z += v0.z; a.w += v0.w;
+        a.x += v1.x; a.y += v1.y; a.z += v1.z; a.w += v1.w;
+        a.x += v2.x; a.y += v2.y; a.z += v2.z; a.w += v2.w;
+        a.x += v3.x; a.y += v3.y; a.z += v3.z; a.w += v3.w;
+      }
+      for (; z < s.KS; ++z) {
+        const float4 v = __ldcg(p + (size_t)z * stride4);
+        a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+      }
     }
-    for (; z < s.KS; ++z) {
-      const float4 v = __ldcg(p + (size_t)z * stride4);
-      a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
-    }
-    float* dxo = s.dX + (s.par_step ? (size_t)(*s.par_step & 1) * s.dx_par_stride : 0);
     reinterpret_cast<float4*>(dxo)[i] = a;
   }
 }
@@ -292,7 +303,12 @@ void launch_dx_finish(const Step& s, cudaStream_t st) {
   const size_t total4 = (size_t)s.B * s.D / 4;
   int blocks = (int)((total4 + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  dx_finish_kernel<<<blocks, 256, 0, st>>>(s);
+  switch (s.KS) {
+    case 18: dx_finish_kernel<18><<<blocks, 256, 0, st>>>(s); break;
+    case 9:  dx_finish_kernel<9><<<blocks, 256, 0, st>>>(s); break;
+    case 4:  dx_finish_kernel<4><<<blocks, 256, 0, st>>>(s); break;
+    default: dx_finish_kernel<0><<<blocks, 256, 0, st>>>(s); break;
+  }
 }
 
 }  // namespace asmh
