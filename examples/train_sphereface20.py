@@ -1,0 +1,102 @@
+#!/usr/bin/env python
+"""End-to-end glue (BASELINE config 2): a stock torch/cuDNN
+restatement of the reference's SphereFaceNet-20 backbone (nets/sphere.py:23-76) feeding the
+B200 A-softmax head, driven like the reference's train loop (train.py:223-250).
+
+    python examples/train_sphereface20.py --steps 20 --batch 512 --classes 10572
+
+Only the head is this repository's product; the backbone is ordinary PyTorch (the survey
+marks backbones out of scope) and exists to show where the head plugs in:
+  features = backbone(images)                                   nets/sphere.py:82
+  loss, _, dX, _ = asoftmax_head(features, labels, C, m, lambda, weights=W, optimizer=opt)
+  features.backward(dX)                                         data_parallel.py:32-38
+Synthetic 112x96 faces; prints loss and images/s like train.py:231-239.
+"""
+import argparse
+import os
+import sys
+import time
+
+import torch
+import torch.nn as nn
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from tf_face_toolbox_b200 import FusedOptimizer, LambdaState, asoftmax_head  # noqa: E402
+
+
+class ResBlock(nn.Module):
+    """Two 3x3 convs with PReLU and an identity shortcut (nets/sphere.py:38-45)."""
+
+    def __init__(self, ch):
+        super().__init__()
+        self.c1, self.a1 = nn.Conv2d(ch, ch, 3, padding=1), nn.PReLU(ch)
+        self.c2, self.a2 = nn.Conv2d(ch, ch, 3, padding=1), nn.PReLU(ch)
+
+    def forward(self, x):
+        return x + self.a2(self.c2(self.a1(self.c1(x))))
+
+
+class SphereFaceNet20(nn.Module):
+    """Stages [64,128,256,512], each a stride-2 3x3 conv + {1,2,4,1} residual blocks, then
+    flatten -> FC 512 (nets/sphere.py:47-76).  112x96 input -> 7x6x512 -> 512-d embedding."""
+
+    def __init__(self, emb=512):
+        super().__init__()
+        layers, cin = [], 3
+        for ch, nblk in zip((64, 128, 256, 512), (1, 2, 4, 1)):
+            layers += [nn.Conv2d(cin, ch, 3, stride=2, padding=1), nn.PReLU(ch)]
+            layers += [ResBlock(ch) for _ in range(nblk)]
+            cin = ch
+        self.body = nn.Sequential(*layers)
+        self.fc = nn.Linear(512 * 7 * 6, emb)
+
+    def forward(self, x):
+        return self.fc(torch.flatten(self.body(x), 1))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--batch", type=int, default=512)
+    ap.add_argument("--classes", type=int, default=10572)
+    ap.add_argument("--lr", type=float, default=0.05)
+    ap.add_argument("--mode", default="bf16")
+    args = ap.parse_args()
+    dev = torch.device("cuda:0")
+    torch.manual_seed(0)
+    net = SphereFaceNet20().to(dev).to(memory_format=torch.channels_last)
+    opt_backbone = torch.optim.SGD(net.parameters(), lr=args.lr, momentum=0.9, weight_decay=5e-4)
+    W = (torch.randn(512, args.classes, device=dev) * 0.001)          # nets/sphere.py:87
+    opt_head = FusedOptimizer("Momentum", lr=args.lr, weight_decay=5e-4)
+    lam = LambdaState()                                               # global_step clock
+    # a fixed synthetic "dataset" of 4 batches so the loss can actually go down
+    data = [(torch.randn(args.batch, 3, 112, 96, device=dev).contiguous(memory_format=torch.channels_last),
+             torch.randint(0, args.classes, (args.batch,), device=dev, dtype=torch.int32)) for _ in range(4)]
+    losses = []
+    t0 = None
+    for step in range(args.steps):
+        if step == 3:
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+        images, labels = data[step % len(data)]
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            feats = net(images)
+        feats32 = feats.float()
+        loss, _, dX, _ = asoftmax_head(feats32.detach(), labels, args.classes, 4, lam.step(),
+                                       weights=W, mode=args.mode, optimizer=opt_head)
+        opt_backbone.zero_grad(set_to_none=True)
+        feats32.backward(dX)                                          # head gradient into the backbone
+        opt_backbone.step()
+        losses.append(loss)
+        if step % 5 == 0 or step == args.steps - 1:
+            print(f"step {step:4d}  cross_entropy {float(loss):.4f}  lambda {lam.value():.2f}", flush=True)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    print(f"{(args.steps - 3) * args.batch / dt:.1f} images/s  ({1e3 * dt / (args.steps - 3):.1f} ms/batch)")
+    first, last = float(torch.stack(losses[:4]).mean()), float(torch.stack(losses[-4:]).mean())
+    print(f"mean loss first 4 steps {first:.4f} -> last 4 steps {last:.4f}")
+    return first, last
+
+
+if __name__ == "__main__":
+    main()

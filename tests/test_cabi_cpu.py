@@ -60,3 +60,31 @@ def test_no_cpu_fallback(lib):
     X, W, y = torch.randn(4, 64), torch.randn(64, 100), torch.zeros(4, dtype=torch.int32)
     with pytest.raises(RuntimeError):
         asoftmax_head(X, y, 100, 4, 5.0, weights=W, mode="fp32")
+
+
+def test_new_entry_points_validate_arguments_without_a_gpu(lib):
+    """Host-side argument checks of the optimizer / center-loss / NVLink-transport entry points."""
+    # symmetric-memory size: only meaningful for 2..8 ranks, grows with the global batch
+    c2 = _lib.AsmConfig(512, 85742, 42871, 0, 512, 4, _lib.MODE_BF16, 0, 2, None)
+    c8 = _lib.AsmConfig(512, 85742, 10718, 0, 512, 4, _lib.MODE_BF16, 0, 8, None)
+    c1 = _lib.AsmConfig(512, 85742, 85742, 0, 512, 4, _lib.MODE_BF16, 0, 1, None)
+    n2, n8 = lib.asm_p2p_bytes(C.byref(c2)), lib.asm_p2p_bytes(C.byref(c8))
+    assert lib.asm_p2p_bytes(C.byref(c1)) == 0
+    # 2 x (dX [B, D] fp32 + stats) dominate: 2 * 512 * 512 * 4 bytes
+    assert n2 > 2 * 512 * 512 * 4 and n8 > 2 * 512 * 512 * 4 and n2 > n8   # fewer local rows per rank at 8
+    assert lib.asm_p2p_attach(None, None) == _lib.ASM_ERR_INVALID_ARG
+    assert lib.asm_step_p2p(None, None, 0, None, 4, None, 0.0, None, None, None, None) == _lib.ASM_ERR_INVALID_ARG
+    assert lib.asm_set_optimizer(None, None, None, None) == _lib.ASM_ERR_INVALID_ARG
+    assert lib.asm_set_lambda_device(None, None) == _lib.ASM_ERR_INVALID_ARG
+    assert lib.asm_center_loss(None, 4, 8, None, 4, None, 10, 0, 0.9, 1.0, None, None, None, None) == _lib.ASM_ERR_INVALID_ARG
+
+
+def test_python_wrappers_refuse_cpu_tensors():
+    from tf_face_toolbox_b200 import FusedOptimizer
+    from tf_face_toolbox_b200.center import center_loss
+    X, y, cen = torch.randn(4, 8), torch.zeros(4, dtype=torch.int32), torch.zeros(3, 8)
+    with pytest.raises(RuntimeError):
+        center_loss(X, y, cen)
+    opt = FusedOptimizer("Adam", lr=1e-3)
+    assert opt.kind == _lib.OPT_ADAM and opt.beta1 == 0.5 and opt.beta2 == 0.999   # data_parallel.py:193
+    assert FusedOptimizer("Momentum").momentum == 0.9                               # data_parallel.py:191

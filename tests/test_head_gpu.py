@@ -336,3 +336,20 @@ def test_center_loss_gpu_matches_oracle_including_duplicates_and_shards():
     assert float(lA) + float(lB) == pytest.approx(loss_r, rel=1e-5)
     np.testing.assert_allclose(acc.cpu().numpy(), grad_r, rtol=1e-4, atol=1e-9)
     np.testing.assert_allclose(torch.cat([cA, cB]).cpu().numpy(), new_r, rtol=1e-4, atol=1e-6)
+
+
+def test_train_loop_glue_loss_decreases():
+    """§8f-4: torch SphereFaceNet-20 backbone + fused-optimizer head, reference-shaped loop."""
+    import importlib.util
+    import sys as _sys
+    spec = importlib.util.spec_from_file_location(
+        "train_sphereface20", os.path.join(os.path.dirname(os.path.dirname(__file__)), "examples", "train_sphereface20.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    argv = _sys.argv
+    _sys.argv = ["train_sphereface20.py", "--steps", "24", "--batch", "64", "--classes", "1000", "--lr", "0.05"]
+    try:
+        first, last = mod.main()
+    finally:
+        _sys.argv = argv
+    assert np.isfinite(first) and np.isfinite(last) and last < first
