@@ -59,7 +59,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--batch", type=int, default=512)
     ap.add_argument("--classes", type=int, default=10572)
-    ap.add_argument("--lr", type=float, default=0.05)
+    ap.add_argument("--lr", type=float, default=0.01)
     ap.add_argument("--mode", default="bf16")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
@@ -86,6 +86,7 @@ def main():
                                        weights=W, mode=args.mode, optimizer=opt_head)
         opt_backbone.zero_grad(set_to_none=True)
         feats32.backward(dX)                                          # head gradient into the backbone
+        torch.nn.utils.clip_grad_norm_(net.parameters(), 5.0)         # un-normalised synthetic net
         opt_backbone.step()
         losses.append(loss)
         if step % 5 == 0 or step == args.steps - 1:

@@ -347,7 +347,7 @@ def test_train_loop_glue_loss_decreases():
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     argv = _sys.argv
-    _sys.argv = ["train_sphereface20.py", "--steps", "24", "--batch", "64", "--classes", "1000", "--lr", "0.05"]
+    _sys.argv = ["train_sphereface20.py", "--steps", "32", "--batch", "64", "--classes", "1000", "--lr", "0.01"]
     try:
         first, last = mod.main()
     finally:
