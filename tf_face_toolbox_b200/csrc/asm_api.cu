@@ -25,7 +25,7 @@ struct asm_head {
   size_t dx_part_capacity = 0;   // floats
   UmmaMaps maps{};
   int maps_B = -1;
-  UmmaTuning tune{8192, 1024, 2048, 0};
+  UmmaTuning tune{8192, 1024, 2048, 0, 0};
   bool fwd_valid = false;
   // dX branch of the backward (DX + dx_finish) runs on a second stream so that it fills the
   // SMs the DW kernel's tail leaves idle; both only depend on G'' from the BWDG kernel
@@ -86,8 +86,8 @@ Layout make_layout(const asm_config& c, int num_sms) {
   // dX split-K partial capacity: the larger of both paths at B_max, but never less than
   // what a single 128-row tile would use (KS grows when B shrinks).
   const int ks_simt = simt_dx_splits(c.B_max, c.D, L.Cp);
-  const int ks_umma = umma_dx_splits(c.B_max, c.D, L.Cp, num_sms);
-  const int ks_one = c.mode == ASM_MODE_BF16 ? umma_dx_splits(128, c.D, L.Cp, num_sms)
+  const int ks_umma = umma_dx_splits(c.B_max, c.D, L.Cp, num_sms, 1);
+  const int ks_one = c.mode == ASM_MODE_BF16 ? umma_dx_splits(128, c.D, L.Cp, num_sms, 1)
                                              : simt_dx_splits(128, c.D, L.Cp);
   const size_t cap_full = (size_t)(c.mode == ASM_MODE_BF16 ? ks_umma : ks_simt) * B * D;
   const size_t cap_one = (size_t)ks_one * (B < 128 ? B : 128) * D;
@@ -201,8 +201,8 @@ int run_forward(asm_head* h, const float* X, int B, const void* labels, int labe
   if (h->cfg.mode == ASM_MODE_BF16) {
     if ((B + 127) / 128 > h->num_sms)
       return fail(h, ASM_ERR_INVALID_ARG, "batch too large for the tcgen05 forward grid%s", "");
-    s.NT = umma_forward_tiles(B, s.Cp, h->num_sms);
-    s.KS = umma_dx_splits(B, s.D, s.Cp, h->num_sms);
+    s.NT = umma_forward_tiles(B, s.Cp, h->num_sms, (h->tune.cg_mask & 1) ? 2 : 1);
+    s.KS = umma_dx_splits(B, s.D, s.Cp, h->num_sms, (h->tune.cg_mask & 8) ? 2 : 1);
     if (h->maps_B != B) {
       if (!umma_build_maps(&h->maps, s))
         return fail(h, ASM_ERR_CUDA, "cuTensorMapEncodeTiled failed%s", "");
@@ -317,6 +317,7 @@ int asm_create(asm_head** out, const asm_config* cfg) {
   if ((e = getenv("ASM_UMMA_MN_SBO"))) h->tune.mn_sbo = (uint32_t)atoi(e);
   if ((e = getenv("ASM_UMMA_MN_KSTEP"))) h->tune.mn_kstep = (uint32_t)atoi(e);
   if ((e = getenv("ASM_UMMA_DEBUG"))) h->tune.debug_flags = (uint32_t)atoi(e);
+  if ((e = getenv("ASM_UMMA_CG"))) h->tune.cg_mask = (uint32_t)atoi(e);
   if ((e = getenv("ASM_NO_OVERLAP")) && atoi(e)) h->overlap = false;
   if (cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||

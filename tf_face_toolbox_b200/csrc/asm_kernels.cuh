@@ -135,10 +135,11 @@ int simt_dx_splits(int B, int D, int Cp);
 
 // bf16 (tcgen05 / TMEM / TMA) contractions with fused epilogues
 struct UmmaMaps {            // TMA descriptors over the bf16 workspace operands
-  CUtensorMap xb_k, xb_k256, xb_mn, wb_mn, wb_mn32, wb_k, g_k, g_mn, g_st, wb_box;
+  CUtensorMap xb_k, xb_k256, xb_mn, wb_mn, wb_mn32, wb_k, wb_k128, g_k, g_mn, g_st, wb_box;
 };
 struct UmmaTuning {          // MN-major shared-memory descriptor parameters (bytes)
   uint32_t mn_lbo, mn_sbo, mn_kstep;
+  uint32_t cg_mask;          // CTA pairs (cta_group::2) per kernel: bit0 FWD, bit1 BWDG, bit2 DW, bit3 DX
   uint32_t debug_flags;      // bit0: skip epilogue math, bit1: DW without stores, bit2: X-resident forward variant (ASM_UMMA_DEBUG, bring-up only)
 };
 struct UmmaArgs {
@@ -149,10 +150,10 @@ struct UmmaArgs {
 };
 cudaError_t umma_configure();
 bool umma_build_maps(UmmaMaps* m, const Step& s);
-int umma_forward_tiles(int B, int Cp, int num_sms);
-int umma_forward_grid(int B, int Cp, int num_sms);
+int umma_forward_tiles(int B, int Cp, int num_sms, int cg);
+int umma_forward_grid(int B, int Cp, int num_sms, int cg);
 int umma_q_parts(int B);
-int umma_dx_splits(int B, int D, int Cp, int num_sms);
+int umma_dx_splits(int B, int D, int Cp, int num_sms, int cg);
 void launch_umma_forward(const Step& s, const UmmaMaps& m, const UmmaTuning& tu, int num_sms,
                          cudaStream_t st);
 void launch_umma_bwdg(const Step& s, const UmmaMaps& m, const UmmaTuning& tu, int num_sms,

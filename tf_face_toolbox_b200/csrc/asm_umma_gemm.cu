@@ -53,12 +53,14 @@ constexpr float LOG2E = 1.4426950408889634f;
 enum { U_FWD = 0, U_BWDG = 1, U_DW = 2, U_DX = 3, U_FWDR = 4, U_DWOPT = 5 };
 
 // pipeline geometry per kernel kind
-template <int KIND> struct Geo {
+// CG = 2: a CTA pair (cluster of 2, cta_group::2) computes one 256 x 256 tile; each CTA
+// stages its own 128 A rows and HALF of the B tile, so a stage is 32 KB and the ring is 6 deep.
+template <int KIND, int CG = 1> struct Geo {
   static constexpr bool RES = (KIND == U_FWDR);
   static constexpr int KB = RES ? 32 : BK;                 // K elements per pipeline stage
-  static constexpr int NST = RES ? 5 : STAGES;             // pipeline depth
+  static constexpr int NST = RES ? 5 : (CG == 2 ? 6 : STAGES);   // pipeline depth
   static constexpr int A_ST = RES ? 0 : BM * KB * 2;       // A bytes per stage
-  static constexpr int B_ST = BN * KB * 2;                 // B bytes per stage
+  static constexpr int B_ST = BN * KB * 2 / CG;            // B bytes per stage (per CTA)
   static constexpr int ST_B = A_ST + B_ST;
   static constexpr int RES_B = RES ? 8 * A_BYTES : 0;      // resident A block (K <= 512)
   static constexpr int CH_B = 64 * KB * 2;                 // one 64-wide MN-major chunk
@@ -97,11 +99,16 @@ __device__ __noinline__ float fwd_target(float* tgt_s, float* tgt_f, const float
 }
 }  // namespace
 
-template <int KIND>
+template <int KIND, int CG = 1>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
             const __grid_constant__ CUtensorMap mapC, Step s, UmmaArgs g) {
-  using G_ = Geo<KIND>;
+  using G_ = Geo<KIND, CG>;
+  static_assert(CG == 1 || KIND != U_FWDR, "the resident forward is single-CTA");
+  // CTA pair: rank within the cluster, work is distributed over PAIRS
+  const int crank = CG == 2 ? (int)ptx::cluster_ctarank() : 0;
+  const int pair_id = (int)blockIdx.x / CG;
+  const int npairs = (int)gridDim.x / CG;
   constexpr bool IS_FWD = (KIND == U_FWD || KIND == U_FWDR);
   constexpr bool RES = G_::RES;
   constexpr int KB = G_::KB, NST = G_::NST, A_ST = G_::A_ST, ST_B = G_::ST_B;
@@ -142,7 +149,7 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&tfull[a], 1);
-      ptx::mbar_init(&tempty[a], EPI_THREADS);
+      ptx::mbar_init(&tempty[a], (EPI_THREADS / 32) * CG);   // one arrival per epilogue warp
     }
     for (int i = 0; i < 4; ++i) {
       ptx::mbar_init(&wfull[i], 1);
@@ -151,11 +158,12 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
     ptx::fence_barrier_init();
   }
   if (warp == 2) {
-    ptx::tmem_alloc(tmem_ptr, 512);
-    ptx::tmem_relinquish();
+    if (CG == 2) { ptx::tmem_alloc_cg2(tmem_ptr, 512); ptx::tmem_relinquish_cg2(); }
+    else         { ptx::tmem_alloc(tmem_ptr, 512); ptx::tmem_relinquish(); }
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if (CG == 2) ptx::cluster_sync_all();       // the peer's barriers exist before anyone signals
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
@@ -172,7 +180,7 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
     // ------------------------------------------------------------ TMA producer
     if (ptx::elect_one()) {
       uint32_t it = 0;
-      if (RES && (int)blockIdx.x < total) {
+      if (RES && pair_id < total) {
         // the CTA's 128 batch rows of Xb, all of K, loaded once (grid % mt == 0)
         const int nblk = (s.D + 63) / 64;
         ptx::mbar_expect_tx(&wfull[0], nblk * A_BYTES);
@@ -180,19 +188,39 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
           ptx::tma_load_2d(smem + i * A_BYTES, &mapA, &wfull[0], i * 64,
                            ((int)blockIdx.x % g.mt) * BM);
       }
-      for (int u = blockIdx.x; u < total; u += gridDim.x) {
+      for (int u = pair_id; u < total; u += npairs) {
         int z, m_idx, n_idx;
         decode(u, z, m_idx, n_idx);
-        const int m0 = m_idx * BM, n0 = n_idx * BN;
+        const int m0 = (m_idx * CG + crank) * BM, n0 = n_idx * BN;
         const int kb0 = z * g.kb_per, kb1 = min(g.kb_total, kb0 + g.kb_per);
         for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int st = it % NST;
           const uint32_t ph = (it / NST) & 1;
           ptx::mbar_wait(&empty[st], ph ^ 1);
-          ptx::mbar_expect_tx(&full[st], ST_B);
           uint8_t* sA = pipe + st * ST_B;
           uint8_t* sB = sA + A_ST;
           const int k0 = kb * KB;
+          if (CG == 2) {
+            // both CTAs load their A rows and their half of B; all bytes are counted on the
+            // leader's full barrier, which only the leader arms
+            if (crank == 0) ptx::mbar_expect_tx(&full[st], 2 * ST_B);
+            if (A_MN) {
+#pragma unroll
+              for (int c = 0; c < BM / 64; ++c)
+                ptx::tma_load_2d_cg2(sA + c * CH_B, &mapA, &full[st], m0 + c * 64, k0);
+            } else {
+              ptx::tma_load_2d_cg2(sA, &mapA, &full[st], k0, m0);
+            }
+            if (B_MN) {
+#pragma unroll
+              for (int c = 0; c < BN / 128; ++c)
+                ptx::tma_load_2d_cg2(sB + c * CH_B, &mapB, &full[st], n0 + (crank * 2 + c) * 64, k0);
+            } else {
+              ptx::tma_load_2d_cg2(sB, &mapB, &full[st], k0, n0 + crank * (BN / 2));
+            }
+            continue;
+          }
+          ptx::mbar_expect_tx(&full[st], ST_B);
           if (RES) {
             // A is resident
           } else if (A_MN) {
@@ -214,15 +242,15 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
-    if (ptx::elect_one()) {
-      const uint32_t idesc = ptx::make_idesc_bf16(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+    if ((CG == 1 || crank == 0) && ptx::elect_one()) {   // CTA pair: the leader issues for both
+      const uint32_t idesc = ptx::make_idesc_bf16(BM * CG, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
       const uint64_t hiA = A_MN ? g.desc_hi_mn : g.desc_hi_k;
       const uint64_t hiB = B_MN ? g.desc_hi_mn : g.desc_hi_k;
       const uint32_t stepA = A_MN ? g.kstep_mn : 32u;
       const uint32_t stepB = B_MN ? g.kstep_mn : 32u;
       uint32_t it = 0, lt = 0;
-      if (RES && (int)blockIdx.x < total) ptx::mbar_wait(&wfull[0], 0);   // resident Xb landed
-      for (int u = blockIdx.x; u < total; u += gridDim.x, ++lt) {
+      if (RES && pair_id < total) ptx::mbar_wait(&wfull[0], 0);   // resident Xb landed
+      for (int u = pair_id; u < total; u += npairs, ++lt) {
         const int z = u / tiles_mn;
         const int kb0 = z * g.kb_per, kb1 = min(g.kb_total, kb0 + g.kb_per);
         const uint32_t a = lt & 1, aph = (lt >> 1) & 1;
@@ -240,13 +268,20 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
           const uint32_t aB = ptx::smem_u32(pipe + st * ST_B) + A_ST;
 #pragma unroll
           for (int kk = 0; kk < KB / 16; ++kk) {
-            ptx::umma_bf16(d_tmem, ptx::smem_desc(hiA, aA + kk * stepA),
-                           ptx::smem_desc(hiB, aB + kk * stepB), idesc,
-                           (kb > kb0 || kk > 0) ? 1u : 0u);
+            if (CG == 2)
+              ptx::umma_bf16_cg2(d_tmem, ptx::smem_desc(hiA, aA + kk * stepA),
+                                 ptx::smem_desc(hiB, aB + kk * stepB), idesc,
+                                 (kb > kb0 || kk > 0) ? 1u : 0u);
+            else
+              ptx::umma_bf16(d_tmem, ptx::smem_desc(hiA, aA + kk * stepA),
+                             ptx::smem_desc(hiB, aB + kk * stepB), idesc,
+                             (kb > kb0 || kk > 0) ? 1u : 0u);
           }
-          ptx::umma_commit(&empty[st]);     // frees the smem slot when these MMAs retire
+          // frees the smem slot (in both CTAs of a pair) when these MMAs retire
+          if (CG == 2) ptx::umma_commit_cg2(&empty[st]); else ptx::umma_commit(&empty[st]);
         }
-        ptx::umma_commit(&tfull[a]);        // accumulator ready for the epilogue
+        // accumulator ready for the epilogue (of both CTAs of a pair)
+        if (CG == 2) ptx::umma_commit_cg2(&tfull[a]); else ptx::umma_commit(&tfull[a]);
       }
     }
   } else if (warp == 3) {
@@ -256,9 +291,10 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
     // half, so the epilogue never waits on a global load.
     if (KIND == U_DW && !(g.debug_flags & 1) && ptx::elect_one()) {
       uint32_t cc = 0;
-      for (int u = blockIdx.x; u < total; u += gridDim.x) {
+      for (int u = pair_id; u < total; u += npairs) {
         int z, m_idx, n_idx;
         decode(u, z, m_idx, n_idx);
+        m_idx = m_idx * CG + crank;
         for (int c = 0; c < 4; ++c, ++cc) {
           const uint32_t buf = cc & 1, ph = (cc >> 1) & 1;
 #pragma unroll
@@ -290,6 +326,7 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
       if (pu >= total) return;
       int pz, pm, pn;
       decode(pu, pz, pm, pn);
+      pm = pm * CG + crank;
       if (IS_FWD) pre0 = s.inv_c[pn * BN + et];
       if (KIND == U_BWDG) {
         const int i = pn * BN + et;
@@ -311,10 +348,20 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
         for (int t = 4; t < s.MT; ++t) pre5 += qp[(size_t)t * s.Cp];   // batches > 512 rows
       }
     };
-    prefetch_tile(blockIdx.x);
-    for (int u = blockIdx.x; u < total; u += gridDim.x, ++lt) {
+    prefetch_tile(pair_id);
+    // accumulator stage released: one arrival per warp on the (leader's) tmem-empty barrier
+    auto release_acc = [&](uint32_t a) {
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (CG == 2 && crank != 0) ptx::mbar_arrive_cluster(&tempty[a], 0);
+        else ptx::mbar_arrive(&tempty[a]);
+      }
+    };
+    for (int u = pair_id; u < total; u += npairs, ++lt) {
       int z, m_idx, n_idx;
       decode(u, z, m_idx, n_idx);
+      m_idx = m_idx * CG + crank;
       const int m0 = m_idx * BM, n0 = n_idx * BN;
       const uint32_t a = lt & 1, aph = (lt >> 1) & 1;
       const uint32_t taddr =
@@ -326,8 +373,7 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
       if (g.debug_flags & 1) {                // bring-up knob: mainloop only, no epilogue math
         ptx::mbar_wait(&tfull[a], aph);
         ptx::tc_fence_after();
-        ptx::tc_fence_before();
-        ptx::mbar_arrive(&tempty[a]);
+        release_acc(a);
         continue;
       }
 
@@ -346,8 +392,7 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
         if (cp == 0) {                                     \
           ptx::tmem_ld32(taddr + 64, r0);                  \
         } else {                                           \
-          ptx::tc_fence_before();                          \
-          ptx::mbar_arrive(&tempty[a]);                    \
+          release_acc(a);                                  \
         }                                                  \
         process(r1, cp * 2 + 1);                           \
       }
@@ -355,7 +400,7 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
       if (IS_FWD) {
         // ---- thread = batch row, columns = classes.  Stage 1/c_j for the tile in smem.
         v0[et] = pre0;
-        prefetch_tile(u + gridDim.x);
+        prefetch_tile(u + npairs);
         const int row = m0 + lane_row;
         const bool rv = row < s.B;
         const int yl = rv ? s.ylocal[row] : -1;
@@ -426,7 +471,7 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
         v0[et] = pre0;
         v1[et] = pre1;
         v2[et] = pre2;
-        prefetch_tile(u + gridDim.x);
+        prefetch_tile(u + npairs);
         const int j = m0 + lane_row;                          // class (< Cp always)
         const float ic = s.inv_c[j];
         const float icl = ic * LOG2E;
@@ -480,7 +525,7 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
         const int j = m0 + lane_row;
         const bool jv = j < s.C;
         const float coef = -(((pre0 + pre1) + (pre3 + pre4)) + pre5) * pre2 * pre2;
-        prefetch_tile(u + gridDim.x);
+        prefetch_tile(u + npairs);
         const int d_first = n0 + col0;
         ptx::mbar_wait(&tfull[a], aph);
         ptx::tc_fence_after();
@@ -514,7 +559,7 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
         const int j = m0 + lane_row;
         const bool jv = j < s.C;
         const float coef = -(((pre0 + pre1) + (pre3 + pre4)) + pre5) * pre2 * pre2;
-        prefetch_tile(u + gridDim.x);
+        prefetch_tile(u + npairs);
         const int d_first = n0 + col0;
         const OptParams op = s.opt;
         ptx::mbar_wait(&tfull[a], aph);
@@ -563,13 +608,16 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
 #undef ASM_EPILOGUE_CHUNKS
     }
     if (IS_FWD && fwd_row >= 0)
-      s.part[(size_t)fwd_row * s.NT + (blockIdx.x / g.mt) * 2 + half] = make_float2(run_m, run_z);
+      s.part[(size_t)fwd_row * s.NT + (pair_id / g.mt) * 2 + half] = make_float2(run_m, run_z);
   }
 
   if (KIND == U_BWDG && (threadIdx.x == 128 || threadIdx.x == 256)) ptx::bulk_wait0();
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 2) ptx::tmem_dealloc(tmem_base, 512);
+  if (CG == 2) ptx::cluster_sync_all();       // the peer may still be read / signalled by the leader
+  if (warp == 2) {
+    if (CG == 2) ptx::tmem_dealloc_cg2(tmem_base, 512); else ptx::tmem_dealloc(tmem_base, 512);
+  }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -610,22 +658,32 @@ bool encode_map(CUtensorMap* m, const void* base, uint64_t inner, uint64_t outer
 }  // namespace
 
 // FWD grid: a multiple of the number of 128-row tiles so each CTA keeps one set of rows
-int umma_forward_grid(int B, int Cp, int num_sms) {
-  const int mt = (B + BM - 1) / BM;
+// cg = 1: one CTA per tile; cg = 2: CTA pairs (cta_group::2) on 256-row tiles.  The pair kernels
+// are used per kernel kind when the M extent has at least two 128-row tiles.
+static int fwd_cg(int B, int cg) { return (cg == 2 && B > BM) ? 2 : 1; }
+
+// FWD grid: a multiple of the number of row tiles so each CTA keeps one set of rows
+int umma_forward_grid(int B, int Cp, int num_sms, int cg) {
+  cg = fwd_cg(B, cg);
+  const int mt = ((B + BM - 1) / BM + cg - 1) / cg;      // row tiles of 128*cg rows
   const int total = mt * (Cp / BN);
-  const int g = (num_sms / mt) * mt;
-  return g < total ? g : total;
+  const int units = num_sms / cg;                          // CTAs or CTA pairs
+  if (mt > units) return 0;
+  const int g = (units / mt) * mt;
+  return (g < total ? g : total) * cg;
 }
 // (max, sum-exp) partials per row written by FWD: one per column half per CTA of that row tile
-int umma_forward_tiles(int B, int Cp, int num_sms) {
-  const int mt = (B + BM - 1) / BM;
-  return 2 * (umma_forward_grid(B, Cp, num_sms) / mt);
+int umma_forward_tiles(int B, int Cp, int num_sms, int cg) {
+  const int c = fwd_cg(B, cg);
+  const int mt = ((B + BM - 1) / BM + c - 1) / c;
+  return 2 * (umma_forward_grid(B, Cp, num_sms, cg) / c / mt);
 }
 int umma_q_parts(int B) { return 2 * ((B + BN - 1) / BN); }            // 128-row partials
 
-int umma_dx_splits(int B, int D, int Cp, int num_sms) {
-  const int tiles = ((B + BM - 1) / BM) * ((D + BN - 1) / BN);
-  int ks = num_sms / tiles;
+int umma_dx_splits(int B, int D, int Cp, int num_sms, int cg) {
+  const int c = fwd_cg(B, cg);
+  const int tiles = (((B + BM - 1) / BM + c - 1) / c) * ((D + BN - 1) / BN);
+  int ks = (num_sms / c) / tiles;
   const int kb_total = (Cp + BK - 1) / BK;
   if (ks > kb_total) ks = kb_total;
   if (ks < 1) ks = 1;
@@ -643,6 +701,7 @@ bool umma_build_maps(UmmaMaps* m, const Step& s) {
   ok &= encode_map(&m->wb_mn, s.Wb, s.Cp, s.D, s.Cp, 64, 64);   // B of FWD / A of BWDG (MN-major)
   ok &= encode_map(&m->wb_mn32, s.Wb, s.Cp, s.D, s.Cp, 64, 32); // B of FWDR (32-deep K stages)
   ok &= encode_map(&m->wb_k, s.Wb, s.Cp, s.D, s.Cp, 64, 256);   // B of DX   (K-major, N = d)
+  ok &= encode_map(&m->wb_k128, s.Wb, s.Cp, s.D, s.Cp, 64, 128);  // B half of DX in a CTA pair
   // G'' [B, Cp]
   ok &= encode_map(&m->g_k, s.G, s.Cp, s.B, s.Cp, 64, 128);     // A of DX   (K-major, M = batch)
   ok &= encode_map(&m->g_mn, s.G, s.Cp, s.B, s.Cp, 64, 64);     // A of DW   (MN-major, M = class)
@@ -661,72 +720,112 @@ static UmmaArgs base_args(const UmmaTuning& tu) {
   return g;
 }
 
+namespace {
+template <int KIND, int CG>
+cudaError_t set_smem() {
+  return cudaFuncSetAttribute(umma_kernel<KIND, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              Geo<KIND, CG>::SMEM);
+}
+// launch with `units` work units (CTAs, or CTA pairs as clusters of 2)
+template <int KIND, int CG>
+void launch_k(int units, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c,
+              const Step& s, const UmmaArgs& g, cudaStream_t st) {
+  if (units <= 0) return;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(units * CG);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = Geo<KIND, CG>::SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = CG == 2 ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, umma_kernel<KIND, CG>, a, b, c, s, g);
+}
+}  // namespace
+
 cudaError_t umma_configure() {
   cudaError_t e;
-  e = cudaFuncSetAttribute(umma_kernel<U_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<U_FWD>::SMEM);
-  if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(umma_kernel<U_FWDR>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<U_FWDR>::SMEM);
-  if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(umma_kernel<U_BWDG>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<U_BWDG>::SMEM);
-  if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(umma_kernel<U_DW>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<U_DW>::SMEM);
-  if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(umma_kernel<U_DWOPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<U_DWOPT>::SMEM);
-  if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(umma_kernel<U_DX>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<U_DX>::SMEM);
+  if ((e = set_smem<U_FWD, 1>()) != cudaSuccess) return e;
+  if ((e = set_smem<U_FWD, 2>()) != cudaSuccess) return e;
+  if ((e = set_smem<U_FWDR, 1>()) != cudaSuccess) return e;
+  if ((e = set_smem<U_BWDG, 1>()) != cudaSuccess) return e;
+  if ((e = set_smem<U_BWDG, 2>()) != cudaSuccess) return e;
+  if ((e = set_smem<U_DW, 1>()) != cudaSuccess) return e;
+  if ((e = set_smem<U_DW, 2>()) != cudaSuccess) return e;
+  if ((e = set_smem<U_DWOPT, 1>()) != cudaSuccess) return e;
+  if ((e = set_smem<U_DWOPT, 2>()) != cudaSuccess) return e;
+  if ((e = set_smem<U_DX, 1>()) != cudaSuccess) return e;
+  return set_smem<U_DX, 2>();
 }
 
 void launch_umma_forward(const Step& s, const UmmaMaps& m, const UmmaTuning& tu, int num_sms,
                          cudaStream_t st) {
   UmmaArgs g = base_args(tu);   // S = Xb Wb: lanes = batch rows, columns = classes
-  g.mt = (s.B + BM - 1) / BM;
+  const int cg = fwd_cg(s.B, (tu.cg_mask & 1) ? 2 : 1);
+  g.mt = ((s.B + BM - 1) / BM + cg - 1) / cg;
   g.nt = s.Cp / BN;
-  const int grid = umma_forward_grid(s.B, s.Cp, num_sms);
-  if (s.D <= 512 && (tu.debug_flags & 4)) {   // opt-in: measured slower (55 vs 48 us at cfg 3)
+  const int units = umma_forward_grid(s.B, s.Cp, num_sms, cg) / cg;
+  if (s.D <= 512 && (tu.debug_flags & 4) && cg == 1) {   // opt-in: measured slower (55 vs 48 us)
     // Xb row tile resident in shared memory, weights stream in 32-deep K stages
     g.kb_total = (s.D + 31) / 32;
     g.kb_per = g.kb_total;
     g.desc_hi_mn = ptx::make_smem_desc_hi(Geo<U_FWDR>::CH_B, tu.mn_sbo);   // chunk stride 4 KB
-    umma_kernel<U_FWDR><<<grid, NUM_THREADS, Geo<U_FWDR>::SMEM, st>>>(m.xb_k, m.wb_mn32, m.wb_mn32, s, g);
+    launch_k<U_FWDR, 1>(units, m.xb_k, m.wb_mn32, m.wb_mn32, s, g, st);
     return;
   }
   g.kb_total = (s.D + BK - 1) / BK;
   g.kb_per = g.kb_total;
-  umma_kernel<U_FWD><<<grid, NUM_THREADS, Geo<U_FWD>::SMEM, st>>>(m.xb_k, m.wb_mn, m.wb_mn, s, g);
+  if (cg == 2) launch_k<U_FWD, 2>(units, m.xb_k, m.wb_mn, m.wb_mn, s, g, st);
+  else launch_k<U_FWD, 1>(units, m.xb_k, m.wb_mn, m.wb_mn, s, g, st);
 }
 
 void launch_umma_bwdg(const Step& s, const UmmaMaps& m, const UmmaTuning& tu, int num_sms,
                       cudaStream_t st) {
   UmmaArgs g = base_args(tu);   // recompute S^T -> G'' (bf16) + q_part: lanes = classes
-  g.mt = s.Cp / BM;
+  const int cg = (tu.cg_mask & 2) ? 2 : 1;
+  g.mt = s.Cp / (BM * cg);
   g.nt = (s.B + BN - 1) / BN;
   g.kb_total = (s.D + BK - 1) / BK;
   g.kb_per = g.kb_total;
-  umma_kernel<U_BWDG><<<min(g.mt * g.nt, num_sms), NUM_THREADS, Geo<U_BWDG>::SMEM, st>>>(m.wb_mn, m.xb_k256, m.g_st, s, g);
+  const int units = min(g.mt * g.nt, num_sms / cg);
+  if (cg == 2) launch_k<U_BWDG, 2>(units, m.wb_mn, m.xb_k, m.g_st, s, g, st);
+  else launch_k<U_BWDG, 1>(units, m.wb_mn, m.xb_k256, m.g_st, s, g, st);
 }
 
 void launch_umma_dw(const Step& s, const UmmaMaps& m, const UmmaTuning& tu, int num_sms,
                     cudaStream_t st) {
   UmmaArgs g = base_args(tu);   // dW^T = G''^T Xb - correction: lanes = classes, columns = d
-  g.mt = s.Cp / BM;
+  const int cg = (tu.cg_mask & 4) ? 2 : 1;
+  g.mt = s.Cp / (BM * cg);
   g.nt = (s.D + BN - 1) / BN;
   g.kb_total = (s.B + BK - 1) / BK;
   g.kb_per = g.kb_total;
-  if (s.opt.kind != 0)
-    umma_kernel<U_DWOPT><<<min(g.mt * g.nt, num_sms), NUM_THREADS, Geo<U_DWOPT>::SMEM, st>>>(m.g_mn, m.xb_mn, m.wb_box, s, g);
-  else
-    umma_kernel<U_DW><<<min(g.mt * g.nt, num_sms), NUM_THREADS, Geo<U_DW>::SMEM, st>>>(m.g_mn, m.xb_mn, m.wb_box, s, g);
+  const int units = min(g.mt * g.nt, num_sms / cg);
+  if (s.opt.kind != 0) {
+    if (cg == 2) launch_k<U_DWOPT, 2>(units, m.g_mn, m.xb_mn, m.wb_box, s, g, st);
+    else launch_k<U_DWOPT, 1>(units, m.g_mn, m.xb_mn, m.wb_box, s, g, st);
+  } else {
+    if (cg == 2) launch_k<U_DW, 2>(units, m.g_mn, m.xb_mn, m.wb_box, s, g, st);
+    else launch_k<U_DW, 1>(units, m.g_mn, m.xb_mn, m.wb_box, s, g, st);
+  }
 }
 
 void launch_umma_dx(const Step& s, const UmmaMaps& m, const UmmaTuning& tu, int num_sms,
                     cudaStream_t st) {
   UmmaArgs g = base_args(tu);   // dX partials = G'' Wb^T, split over the classes
-  g.mt = (s.B + BM - 1) / BM;
+  const int cg = fwd_cg(s.B, (tu.cg_mask & 8) ? 2 : 1);
+  g.mt = ((s.B + BM - 1) / BM + cg - 1) / cg;
   g.nt = (s.D + BN - 1) / BN;
   g.kb_total = (s.Cp + BK - 1) / BK;
   g.ks = s.KS;
   g.kb_per = (g.kb_total + g.ks - 1) / g.ks;
-  umma_kernel<U_DX><<<min(g.mt * g.nt * g.ks, num_sms), NUM_THREADS, Geo<U_DX>::SMEM, st>>>(m.g_k, m.wb_k, m.wb_k, s, g);
+  const int units = min(g.mt * g.nt * g.ks, num_sms / cg);
+  if (cg == 2) launch_k<U_DX, 2>(units, m.g_k, m.wb_k128, m.wb_k128, s, g, st);
+  else launch_k<U_DX, 1>(units, m.g_k, m.wb_k, m.wb_k, s, g, st);
 }
 
 }  // namespace asmh
