@@ -25,7 +25,7 @@ struct asm_head {
   size_t dx_part_capacity = 0;   // floats
   UmmaMaps maps{};
   int maps_B = -1;
-  UmmaTuning tune{8192, 1024, 2048, 0, 0};
+  UmmaTuning tune{8192, 1024, 2048, 15, 0};   // CTA pairs on all four kernels (ASM_UMMA_CG=0: single-CTA)
   bool fwd_valid = false;
   // dX branch of the backward (DX + dx_finish) runs on a second stream so that it fills the
   // SMs the DW kernel's tail leaves idle; both only depend on G'' from the BWDG kernel
