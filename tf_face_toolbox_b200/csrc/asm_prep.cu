@@ -17,7 +17,7 @@ namespace asmh {
 //   blocks [nwb, ...): X role. One warp per embedding row: n_i, 1/n_i, bf16 copy, and the
 //     label -> local-class-index translation with the range check.
 // ---------------------------------------------------------------------------------------
-template <bool VEC2, bool BF16, int TX, int TY>
+template <bool VEC2, bool BF16, int TX, int TY, int U>
 __global__ void __launch_bounds__(256) prep_kernel(Step s, const void* labels, int label_bytes,
                                                    int nwb) {
   static_assert(TX * TY == 256, "256 threads");
@@ -33,7 +33,6 @@ __global__ void __launch_bounds__(256) prep_kernel(Step s, const void* labels, i
       __nv_bfloat16* wb = BF16 ? s.Wb + j0 : nullptr;
       // U rows per trip: all loads are issued before the first use so that U x 8 B per
       // thread are in flight (the bf16 stores would otherwise serialise the loads).
-      constexpr int U = 16;
       for (int d0 = ty; d0 < s.D; d0 += TY * U) {
         float x0[U], x1[U];
 #pragma unroll
@@ -102,30 +101,35 @@ __global__ void __launch_bounds__(256) prep_kernel(Step s, const void* labels, i
   }
 }
 
-template <int TX, int TY>
+template <int TX, int TY, int U>
 static void launch_prep_t(const Step& s, const void* labels, int label_bytes, cudaStream_t st) {
   const int nwb = (s.Cp + 2 * TX - 1) / (2 * TX);
   const int nxb = (s.B + 7) / 8;
   const bool vec2 = (s.C % 2 == 0) && ((reinterpret_cast<uintptr_t>(s.W) & 7) == 0);
   dim3 grd(nwb + nxb);
   if (s.mode == 1) {
-    if (vec2) prep_kernel<true, true, TX, TY><<<grd, 256, 0, st>>>(s, labels, label_bytes, nwb);
-    else prep_kernel<false, true, TX, TY><<<grd, 256, 0, st>>>(s, labels, label_bytes, nwb);
+    if (vec2) prep_kernel<true, true, TX, TY, U><<<grd, 256, 0, st>>>(s, labels, label_bytes, nwb);
+    else prep_kernel<false, true, TX, TY, U><<<grd, 256, 0, st>>>(s, labels, label_bytes, nwb);
   } else {
-    if (vec2) prep_kernel<true, false, TX, TY><<<grd, 256, 0, st>>>(s, labels, label_bytes, nwb);
-    else prep_kernel<false, false, TX, TY><<<grd, 256, 0, st>>>(s, labels, label_bytes, nwb);
+    if (vec2) prep_kernel<true, false, TX, TY, U><<<grd, 256, 0, st>>>(s, labels, label_bytes, nwb);
+    else prep_kernel<false, false, TX, TY, U><<<grd, 256, 0, st>>>(s, labels, label_bytes, nwb);
   }
 }
 
 void launch_prep(const Step& s, const void* labels, int label_bytes, cudaStream_t st) {
-  static int shape = -1;                       // ASM_PREP_SHAPE: 0 = 32x8, 1 = 128x2, 2 = 256x1
+  // Block shape (column pairs x row groups) and loads in flight per thread.  Measured at
+  // cfg 3 (263.9 MB): 32x8/U=4 51.7 us (5.1 TB/s), 16x16/U=8 51.7, 32x8/U=8 53.2,
+  // 32x8/U=16 59.8, 32x8/U=32 94, 32x8/U=2 65, 128x2/U=16 73: occupancy beats unroll depth,
+  // and wider per-block column spans do not help.  ASM_PREP_SHAPE selects the alternatives.
+  static int shape = -1;
   if (shape < 0) {
     const char* e = getenv("ASM_PREP_SHAPE");
     shape = e ? atoi(e) : 0;
   }
-  if (shape == 1) launch_prep_t<128, 2>(s, labels, label_bytes, st);
-  else if (shape == 2) launch_prep_t<256, 1>(s, labels, label_bytes, st);
-  else launch_prep_t<32, 8>(s, labels, label_bytes, st);
+  if (shape == 1) launch_prep_t<32, 8, 16>(s, labels, label_bytes, st);
+  else if (shape == 2) launch_prep_t<16, 16, 8>(s, labels, label_bytes, st);
+  else if (shape == 3) launch_prep_t<128, 2, 16>(s, labels, label_bytes, st);
+  else launch_prep_t<32, 8, 4>(s, labels, label_bytes, st);
 }
 
 // ---------------------------------------------------------------------------------------
