@@ -34,7 +34,7 @@ constexpr int STAGE_BYTES = A_BYTES + B_BYTES; // 48 KB
 constexpr int CHUNK_BYTES = 64 * BK * 2;       // one 64-wide MN-major chunk: 8 KB
 constexpr int NUM_THREADS = 384;
 constexpr int EPI_THREADS = 256;
-constexpr int AUX_BARS = 256;                  // barriers + tmem ptr
+constexpr int AUX_BARS = 512;                  // barriers + tmem ptr
 constexpr int AUX_VEC = 3 * 2 * BN * 4;        // per-tile vectors: 3 arrays x 2 stages x 256
 constexpr int STG_HALF = 32 * 128 * 2;         // G'' staging per column half: 32 rows x 128 classes
 constexpr int AUX_STG = 2 * STG_HALF;          // 16 KB
@@ -58,14 +58,17 @@ enum { U_FWD = 0, U_BWDG = 1, U_DW = 2, U_DX = 3, U_FWDR = 4, U_DWOPT = 5 };
 template <int KIND, int CG = 1> struct Geo {
   static constexpr bool RES = (KIND == U_FWDR);
   static constexpr int KB = RES ? 32 : BK;                 // K elements per pipeline stage
-  static constexpr int NST = RES ? 5 : (CG == 2 ? 6 : STAGES);   // pipeline depth
+  // the dW kernel of a CTA pair trades its 6th operand stage for a 4-deep weight-chunk ring
+  static constexpr int NWB = (KIND == U_DW && CG == 2) ? 4 : 2;  // weight-chunk buffers per column half
+  static constexpr int NST = RES ? 5 : (CG == 2 ? ((KIND == U_DW) ? 5 : 6) : STAGES);   // pipeline depth
   static constexpr int A_ST = RES ? 0 : BM * KB * 2;       // A bytes per stage
   static constexpr int B_ST = BN * KB * 2 / CG;            // B bytes per stage (per CTA)
   static constexpr int ST_B = A_ST + B_ST;
   static constexpr int RES_B = RES ? 8 * A_BYTES : 0;      // resident A block (K <= 512)
   static constexpr int CH_B = 64 * KB * 2;                 // one 64-wide MN-major chunk
   static constexpr int PIPE_B = RES_B + NST * ST_B;
-  static constexpr int SMEM = PIPE_B + AUX_BARS + (RES ? AUX_VEC : AUX_REGION) + 1024;
+  static constexpr int AUX_R = RES ? AUX_VEC : (KIND == U_DW ? 2 * NWB * WB_BUF : AUX_REGION);
+  static constexpr int SMEM = PIPE_B + AUX_BARS + AUX_R + 1024;
   static_assert(SMEM <= 232448, "exceeds the 227 KB shared memory of an sm_100 CTA");
 };
 
@@ -127,8 +130,9 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
   uint64_t* tfull = empty + 8;                                        // [2]
   uint64_t* tempty = tfull + 2;                                       // [2]
   uint64_t* wfull = tempty + 2;                                       // DW: [half][buf]; FWDR: [0] = X resident
-  uint64_t* wempty = wfull + 4;                                       // DW: [half][buf]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(wempty + 4);
+  uint64_t* wempty = wfull + 8;                                       // DW: [half][buf]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(wempty + 8);
+  constexpr int NWB = G_::NWB;
   float* vec0 = reinterpret_cast<float*>(smem + PIPE_B + AUX_BARS);   // [2][BN]
   float* vec1 = vec0 + 2 * BN;
   float* vec2 = vec1 + 2 * BN;
@@ -151,7 +155,7 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
       ptx::mbar_init(&tfull[a], 1);
       ptx::mbar_init(&tempty[a], (EPI_THREADS / 32) * CG);   // one arrival per epilogue warp
     }
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < 8; ++i) {
       ptx::mbar_init(&wfull[i], 1);
       ptx::mbar_init(&wempty[i], 128);
     }
@@ -296,12 +300,12 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
         decode(u, z, m_idx, n_idx);
         m_idx = m_idx * CG + crank;
         for (int c = 0; c < 4; ++c, ++cc) {
-          const uint32_t buf = cc & 1, ph = (cc >> 1) & 1;
+          const uint32_t buf = cc % NWB, ph = (cc / NWB) & 1;
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
-            ptx::mbar_wait(&wempty[h * 2 + buf], ph ^ 1);
-            ptx::mbar_expect_tx(&wfull[h * 2 + buf], WB_BUF);
-            ptx::tma_load_2d(wbuf + (h * 2 + buf) * WB_BUF, &mapC, &wfull[h * 2 + buf],
+            ptx::mbar_wait(&wempty[h * NWB + buf], ph ^ 1);
+            ptx::mbar_expect_tx(&wfull[h * NWB + buf], WB_BUF);
+            ptx::tma_load_2d(wbuf + (h * NWB + buf) * WB_BUF, &mapC, &wfull[h * NWB + buf],
                              m_idx * BM, n_idx * BN + h * 128 + c * 32);
           }
         }
@@ -531,16 +535,16 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
         ptx::tc_fence_after();
         auto process = [&](const uint32_t (&r)[32], int c) {
           const uint32_t cc = lt * 4 + c;                     // chunk counter of this half
-          const uint32_t buf = cc & 1, ph = (cc >> 1) & 1;
+          const uint32_t buf = cc % NWB, ph = (cc / NWB) & 1;
           const unsigned short* wsm =
-              reinterpret_cast<const unsigned short*>(wbuf + (half * 2 + buf) * WB_BUF) + lane_row;
-          ptx::mbar_wait(&wfull[half * 2 + buf], ph);
+              reinterpret_cast<const unsigned short*>(wbuf + (half * NWB + buf) * WB_BUF) + lane_row;
+          ptx::mbar_wait(&wfull[half * NWB + buf], ph);
           float o[32];
 #pragma unroll
           for (int b = 0; b < 32; ++b)
             o[b] = fmaf(__uint_as_float(static_cast<uint32_t>(wsm[b * 128]) << 16), coef,
                         __uint_as_float(r[b]));
-          ptx::mbar_arrive(&wempty[half * 2 + buf]);         // chunk consumed (values in o[])
+          ptx::mbar_arrive(&wempty[half * NWB + buf]);       // chunk consumed (values in o[])
           const int db = d_first + c * 32;                    // first d of the chunk
           if (jv && db < s.D && !(g.debug_flags & 2)) {       // D % 32 == 0 in bf16 mode
             float* dst = s.dW + (size_t)db * s.C + j;
