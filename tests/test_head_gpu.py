@@ -353,3 +353,25 @@ def test_train_loop_glue_loss_decreases():
     finally:
         _sys.argv = argv
     assert np.isfinite(first) and np.isfinite(last) and last < first
+
+
+def test_host_pipelined_step_returns_every_loss_in_order():
+    """HostPipelinedStep: async double-buffered H2D + one-step-late loss read-back gives the
+    same per-step losses as the plain synchronous loop."""
+    from tf_face_toolbox_b200.pipeline import HostPipelinedStep
+    dev = torch.device("cuda:0")
+    W = make_inputs(64, 128, 1000, seed=1).W.to(dev)
+    batches = [make_inputs(64, 128, 1000, seed=100 + i) for i in range(5)]
+    want = []
+    for b in batches:
+        loss, *_ = asoftmax_head(b.X.to(dev), b.y.to(dev), 1000, 4, 5.0, weights=W, mode="fp32")
+        want.append(float(loss))
+    runner = HostPipelinedStep(lambda X, y: (lambda o: (o[0], o[2], o[3]))(
+        asoftmax_head(X, y, 1000, 4, 5.0, weights=W, mode="fp32")), 64, 128, dev)
+    got = []
+    for b in batches:
+        prev = runner.submit(b.X.pin_memory(), b.y.pin_memory())
+        if prev is not None:
+            got.append(prev)
+    got.append(runner.flush())
+    assert got == want
