@@ -32,6 +32,7 @@ struct asm_head {
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool overlap = true;           // ASM_NO_OVERLAP=1 disables
+  bool pdl = true;               // programmatic dependent launch between the step's kernels (ASM_PDL=0 disables)
   // NVLink peer-memory transport (asm_p2p_attach / asm_step_p2p)
   P2P p2p{};
   bool p2p_ready = false;
@@ -180,6 +181,12 @@ int run_forward(asm_head* h, const float* X, int B, const void* labels, int labe
   s.MT = h->cfg.mode == ASM_MODE_BF16 ? umma_q_parts(B) : (B + kRowTileHost - 1) / kRowTileHost;
   h->launches = 0;
   h->n_marks = 0;
+  {
+    // no programmatic edges inside a graph capture, none while per-kernel events are recorded
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(stream, &cs);
+    s.pdl = (h->pdl && !h->profiling && cs == cudaStreamCaptureStatusNone) ? 1 : 0;
+  }
   h->fwd_valid = false;
   CU_TRY(h, cudaMemsetAsync(s.flags, 0, 4, stream));
   if (h->l2_persist_bytes && h->cfg.mode == ASM_MODE_BF16 && (!h->l2_set || h->l2_stream != stream)) {
@@ -319,6 +326,7 @@ int asm_create(asm_head** out, const asm_config* cfg) {
   if ((e = getenv("ASM_UMMA_DEBUG"))) h->tune.debug_flags = (uint32_t)atoi(e);
   if ((e = getenv("ASM_UMMA_CG"))) h->tune.cg_mask = (uint32_t)atoi(e);
   if ((e = getenv("ASM_NO_OVERLAP")) && atoi(e)) h->overlap = false;
+  if ((e = getenv("ASM_PDL"))) h->pdl = atoi(e) != 0;
   if (cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess) {

@@ -53,6 +53,14 @@ __device__ __forceinline__ float step_lambda(float by_value, const float* dev) {
   return dev ? __ldg(dev) : by_value;
 }
 
+// Programmatic dependent launch (PDL).  pdl_trigger(): the next kernel in the stream may
+// start launching (its CTAs become resident as SMs free up and run their prologue).
+// pdl_wait(): blocks until the previous kernel has completed and its writes are visible --
+// required before touching anything a predecessor produced.  Both are no-ops for a kernel
+// that was launched without the programmatic-serialization attribute.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // Online-softmax pair combine: (m, z) <- (m, z) (+) (m2, z2)
 __device__ __forceinline__ void ms_combine(float& m, float& z, float m2, float z2) {
   const float mn = fmaxf(m, m2);

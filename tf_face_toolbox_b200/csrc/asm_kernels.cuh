@@ -66,6 +66,36 @@ void launch_p2p_gather_x(const P2P& p, float* Xg, int* yg, int D, cudaStream_t s
 void launch_p2p_gather_stats(const P2P& p, float* stats_all, int B, cudaStream_t st);
 void launch_p2p_reduce_dx(const P2P& p, float* dX_local, int D, cudaStream_t st);
 
+// Launch with the programmatic-stream-serialization attribute when `pdl` is set (never while
+// the stream is being captured into a graph): the kernel may start while its predecessor
+// drains, and orders itself with pdl_wait().
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                       bool pdl, int cluster, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (cluster > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = cluster;
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (pdl) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 constexpr int kRowTileHost = 128;   // == asmh::kRowTile (asm_common.cuh)
 
 struct Step {
@@ -111,6 +141,7 @@ struct Step {
   // P2P transport: outputs that live in the parity-double-buffered symmetric block are
   // addressed as base + (*par_step & 1) * stride on the device (CUDA-graph friendly)
   const unsigned* par_step;
+  int pdl;                   // launch dependents programmatically (eager, non-captured streams)
   size_t stats_par_stride, dx_par_stride;   // in floats
 };
 

@@ -21,6 +21,7 @@ template <bool VEC2, bool BF16, int TX, int TY, int U>
 __global__ void __launch_bounds__(256) prep_kernel(Step s, const void* labels, int label_bytes,
                                                    int nwb) {
   static_assert(TX * TY == 256, "256 threads");
+  pdl_trigger();            // first kernel of the step: nothing to wait for
   __shared__ float red[TY][2 * TX];
   const int tid = threadIdx.x;
   if ((int)blockIdx.x < nwb) {
@@ -136,6 +137,8 @@ void launch_prep(const Step& s, const void* labels, int label_bytes, cudaStream_
 // combine_local: one warp per row reduces the per-column-tile (max, sumexp) partials.
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) combine_local_kernel(Step s) {
+  pdl_trigger();
+  pdl_wait();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= s.B) return;
@@ -160,7 +163,7 @@ __global__ void __launch_bounds__(256) combine_local_kernel(Step s) {
 }
 
 void launch_combine_local(const Step& s, cudaStream_t st) {
-  combine_local_kernel<<<(s.B + 7) / 8, 256, 0, st>>>(s);
+  launch_pdl(combine_local_kernel, dim3((s.B + 7) / 8), dim3(256), 0, st, s.pdl != 0, 1, s);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -178,6 +181,8 @@ template <bool FUSED>
 __global__ void __launch_bounds__(256) combine_kernel(Step s, const float* stats_all, int n_shards) {
   __shared__ float red[256];
   __shared__ bool is_last;
+  pdl_trigger();
+  pdl_wait();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row < s.B) {
@@ -252,11 +257,12 @@ __global__ void __launch_bounds__(256) combine_kernel(Step s, const float* stats
 }
 
 void launch_combine_global(const Step& s, const float* stats_all, int n_shards, cudaStream_t st) {
-  combine_kernel<false><<<(s.B + 7) / 8, 256, 0, st>>>(s, stats_all, n_shards);
+  launch_pdl(combine_kernel<false>, dim3((s.B + 7) / 8), dim3(256), 0, st, false, 1, s, stats_all, n_shards);
 }
 
 void launch_combine_fused(const Step& s, cudaStream_t st) {
-  combine_kernel<true><<<(s.B + 7) / 8, 256, 0, st>>>(s, nullptr, 1);
+  launch_pdl(combine_kernel<true>, dim3((s.B + 7) / 8), dim3(256), 0, st, s.pdl != 0, 1, s,
+             static_cast<const float*>(nullptr), 1);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -266,6 +272,8 @@ void launch_combine_fused(const Step& s, cudaStream_t st) {
 // KS_T == 0: generic loop in batches of four.  Summation order z = 0..KS-1 either way.
 template <int KS_T>
 __global__ void __launch_bounds__(256) dx_finish_kernel(Step s) {
+  pdl_trigger();
+  pdl_wait();
   const size_t total4 = (size_t)s.B * s.D / 4;
   const size_t stride4 = total4;
   float* dxo = s.dX + (s.par_step ? (size_t)(*s.par_step & 1) * s.dx_par_stride : 0);
@@ -308,10 +316,10 @@ void launch_dx_finish(const Step& s, cudaStream_t st) {
   int blocks = (int)((total4 + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
   switch (s.KS) {
-    case 18: dx_finish_kernel<18><<<blocks, 256, 0, st>>>(s); break;
-    case 9:  dx_finish_kernel<9><<<blocks, 256, 0, st>>>(s); break;
-    case 4:  dx_finish_kernel<4><<<blocks, 256, 0, st>>>(s); break;
-    default: dx_finish_kernel<0><<<blocks, 256, 0, st>>>(s); break;
+    case 18: launch_pdl(dx_finish_kernel<18>, dim3(blocks), dim3(256), 0, st, s.pdl != 0, 1, s); break;
+    case 9:  launch_pdl(dx_finish_kernel<9>, dim3(blocks), dim3(256), 0, st, s.pdl != 0, 1, s); break;
+    case 4:  launch_pdl(dx_finish_kernel<4>, dim3(blocks), dim3(256), 0, st, s.pdl != 0, 1, s); break;
+    default: launch_pdl(dx_finish_kernel<0>, dim3(blocks), dim3(256), 0, st, s.pdl != 0, 1, s); break;
   }
 }
 

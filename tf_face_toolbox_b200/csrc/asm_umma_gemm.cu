@@ -107,6 +107,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
             const __grid_constant__ CUtensorMap mapC, Step s, UmmaArgs g) {
   using G_ = Geo<KIND, CG>;
+  pdl_trigger();      // the next kernel's CTAs may take over SMs as this grid's tail drains
   static_assert(CG == 1 || KIND != U_FWDR, "the resident forward is single-CTA");
   // CTA pair: rank within the cluster, work is distributed over PAIRS
   const int crank = CG == 2 ? (int)ptx::cluster_ctarank() : 0;
@@ -170,6 +171,9 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
   if (CG == 2) ptx::cluster_sync_all();       // the peer's barriers exist before anyone signals
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  // prologue done (barriers, TMEM, descriptor prefetch overlapped the predecessor's tail);
+  // from here on the kernel reads what earlier kernels wrote
+  pdl_wait();
 
   const int tiles_mn = g.mt * g.nt;
   const int total = tiles_mn * g.ks;
@@ -735,19 +739,10 @@ template <int KIND, int CG>
 void launch_k(int units, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c,
               const Step& s, const UmmaArgs& g, cudaStream_t st) {
   if (units <= 0) return;
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(units * CG);
-  cfg.blockDim = dim3(NUM_THREADS);
-  cfg.dynamicSmemBytes = Geo<KIND, CG>::SMEM;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CG;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = CG == 2 ? 1 : 0;
-  cudaLaunchKernelEx(&cfg, umma_kernel<KIND, CG>, a, b, c, s, g);
+  // DW follows an event record (the dX fork), everything else follows a kernel directly
+  const bool pdl = s.pdl != 0 && KIND != U_DW && KIND != U_DWOPT;
+  launch_pdl(umma_kernel<KIND, CG>, dim3(units * CG), dim3(NUM_THREADS), Geo<KIND, CG>::SMEM, st, pdl,
+             CG, a, b, c, s, g);
 }
 }  // namespace
 
