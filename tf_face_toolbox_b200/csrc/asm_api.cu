@@ -25,6 +25,7 @@ struct asm_head {
   size_t dx_part_capacity = 0;   // floats
   UmmaMaps maps{};
   int maps_B = -1;
+  bool tc = false;               // tcgen05 kernels (bf16 mode, or fp32 mode through bf16 planes)
   UmmaTuning tune{8192, 1024, 2048, 15, 0};   // CTA pairs on all four kernels (ASM_UMMA_CG=0: single-CTA)
   bool fwd_valid = false;
   // dX branch of the backward (DX + dx_finish) runs on a second stream so that it fills the
@@ -77,8 +78,19 @@ bool valid_cfg(const asm_config* c) {
   return true;
 }
 
+// fp32 mode runs on the tensor cores (operands split into bf16 planes, "x3") whenever the
+// tcgen05 tiling applies; ASM_FP32_SIMT=1 forces the CUDA-core kernels.
+bool use_x3(const asm_config& c) {
+  if (c.mode != ASM_MODE_FP32 || c.D % 64 != 0) return false;
+  const char* e = getenv("ASM_FP32_SIMT");
+  return !(e && atoi(e) != 0);
+}
+bool use_tc(const asm_config& c) { return c.mode == ASM_MODE_BF16 || use_x3(c); }
+
 Layout make_layout(const asm_config& c, int num_sms) {
   Layout L{};
+  const bool tc = use_tc(c);
+  const size_t planes = use_x3(c) ? 3 : 1;
   const size_t B = c.B_max, D = c.D;
   L.Cp = (int)align_up(c.C_local, 256);
   L.NT = (L.Cp + 127) / 128;
@@ -88,9 +100,9 @@ Layout make_layout(const asm_config& c, int num_sms) {
   // what a single 128-row tile would use (KS grows when B shrinks).
   const int ks_simt = simt_dx_splits(c.B_max, c.D, L.Cp);
   const int ks_umma = umma_dx_splits(c.B_max, c.D, L.Cp, num_sms, 1);
-  const int ks_one = c.mode == ASM_MODE_BF16 ? umma_dx_splits(128, c.D, L.Cp, num_sms, 1)
-                                             : simt_dx_splits(128, c.D, L.Cp);
-  const size_t cap_full = (size_t)(c.mode == ASM_MODE_BF16 ? ks_umma : ks_simt) * B * D;
+  const int ks_one = tc ? umma_dx_splits(128, c.D, L.Cp, num_sms, 1)
+                        : simt_dx_splits(128, c.D, L.Cp);
+  const size_t cap_full = (size_t)(tc ? ks_umma : ks_simt) * B * D;
   const size_t cap_one = (size_t)ks_one * (B < 128 ? B : 128) * D;
   L.dx_capacity = cap_full > cap_one ? cap_full : cap_one;
   size_t off = 0;
@@ -113,9 +125,9 @@ Layout make_layout(const asm_config& c, int num_sms) {
   L.q_part = take((size_t)L.MT * L.Cp * 4);
   L.G = take(B * (size_t)L.Cp * (c.mode == ASM_MODE_BF16 ? 2 : 4));
   L.dx_part = take(L.dx_capacity * 4);
-  if (c.mode == ASM_MODE_BF16) {
-    L.Xb = take(B * D * 2);
-    L.Wb = take(D * (size_t)L.Cp * 2);
+  if (tc) {
+    L.Xb = take(planes * B * D * 2);
+    L.Wb = take(planes * D * (size_t)L.Cp * 2);
   }
   if (c.world > 1) {
     L.Xg = take(B * D * 4);
@@ -178,7 +190,7 @@ int run_forward(asm_head* h, const float* X, int B, const void* labels, int labe
   s.X = X;
   s.W = W;
   s.logits = logits;
-  s.MT = h->cfg.mode == ASM_MODE_BF16 ? umma_q_parts(B) : (B + kRowTileHost - 1) / kRowTileHost;
+  s.MT = h->tc ? umma_q_parts(B) : (B + kRowTileHost - 1) / kRowTileHost;
   h->launches = 0;
   h->n_marks = 0;
   {
@@ -205,7 +217,7 @@ int run_forward(asm_head* h, const float* X, int B, const void* labels, int labe
     h->l2_set = true;
     h->l2_stream = stream;
   }
-  if (h->cfg.mode == ASM_MODE_BF16) {
+  if (h->tc) {
     if ((B + 127) / 128 > h->num_sms)
       return fail(h, ASM_ERR_INVALID_ARG, "batch too large for the tcgen05 forward grid%s", "");
     s.NT = umma_forward_tiles(B, s.Cp, h->num_sms, (h->tune.cg_mask & 1) ? 2 : 1);
@@ -223,7 +235,7 @@ int run_forward(asm_head* h, const float* X, int B, const void* labels, int labe
   mark(h, "prep_norms", stream);
   launch_prep(s, labels, label_bytes, stream);
   mark(h, "fwd_logits_stats", stream);
-  if (h->cfg.mode == ASM_MODE_BF16) launch_umma_forward(s, h->maps, h->tune, h->num_sms, stream);
+  if (h->tc) launch_umma_forward(s, h->maps, h->tune, h->num_sms, stream);
   else launch_simt_forward(s, stream);
   if (want_local_stats) {
     mark(h, "combine_local", stream);
@@ -242,7 +254,7 @@ int run_backward(asm_head* h, const float* stats_all, int n_shards, float* loss_
   s.dX = dX;
   s.dW = dW;
   s.Wmut = const_cast<float*>(s.W);       // only written when an optimizer is armed
-  const bool tc = h->cfg.mode == ASM_MODE_BF16;
+  const bool tc = h->tc;
   if (stats_all) {
     // profiling: the gap between the two halves is the host-side statistics all-gather
     if (h->profiling && h->n_marks > 0 && h->n_marks < asm_head::kMaxMarks)
@@ -343,7 +355,8 @@ int asm_create(asm_head** out, const asm_config* cfg) {
   }
   h->ws_bytes = L.total;
   cudaMemset(h->ws, 0, L.total);
-  if (cfg->mode == ASM_MODE_BF16) {
+  h->tc = use_tc(*cfg);
+  if (h->tc) {
     ce = umma_configure();
     if (ce != cudaSuccess) {
       fail(nullptr, ASM_ERR_CUDA, "cudaFuncSetAttribute(smem): %s", cudaGetErrorString(ce));
@@ -360,6 +373,7 @@ int asm_create(asm_head** out, const asm_config* cfg) {
   s.class_offset = cfg->class_offset;
   s.m = cfg->m;
   s.mode = cfg->mode;
+  s.x3 = use_x3(*cfg) ? 1 : 0;
   char* w = h->ws;
   s.ylocal = (int*)(w + L.ylocal);
   s.flags = (int*)(w + L.flags);
@@ -380,7 +394,7 @@ int asm_create(asm_head** out, const asm_config* cfg) {
   s.G = (void*)(w + L.G);
   s.dx_part = (float*)(w + L.dx_part);
   h->dx_part_capacity = L.dx_capacity;
-  if (cfg->mode == ASM_MODE_BF16) {
+  if (h->tc) {
     s.Xb = (__nv_bfloat16*)(w + L.Xb);
     s.Wb = (__nv_bfloat16*)(w + L.Wb);
   }

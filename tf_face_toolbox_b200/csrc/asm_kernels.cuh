@@ -132,8 +132,13 @@ struct Step {
   void* G;                   // [B, Cp]  G'' = G' * inv_c   (fp32 or bf16 by mode)
   float* dx_part;            // [KS, B, D] split-K partials of dX
   int KS;
-  __nv_bfloat16* Xb;         // [B, D]    bf16 mode
-  __nv_bfloat16* Wb;         // [D, Cp]   bf16 mode
+  __nv_bfloat16* Xb;         // [B, D]    bf16 mode;  [B, 3D]  (three planes side by side) when x3
+  __nv_bfloat16* Wb;         // [D, Cp]   bf16 mode;  [D, 3Cp] when x3
+  // x3 = 1: fp32 mode on the tensor cores.  Every fp32 operand is split exactly into bf16
+  // planes (v = p0 + p1 + p2, p0 = bf16(v), p1 = bf16(v - p0), ...) stored side by side along
+  // the inner dimension; a contraction runs as a chain of plane-pair segments accumulated in
+  // the same fp32 TMEM tile.  G'' then has two planes: [B, 2Cp] bf16.
+  int x3;
   OptParams opt;             // fused optimizer (kind 0 = off: dW is written instead)
   float* Wmut;               // [D, C]  W, updated in place when opt.kind != 0
   float* opt_s0;             // [D, C]  momentum accumulator / adam m
@@ -175,6 +180,10 @@ struct UmmaTuning {          // MN-major shared-memory descriptor parameters (by
 };
 struct UmmaArgs {
   int mt, nt, ks, kb_total, kb_per;
+  // plane-pair segments of the K loop (x3): K block kb belongs to segment kb / kb_seg, whose
+  // operands start segA / segB elements further along the inner dimension of their tensors
+  int nseg, kb_seg;
+  int segA[6], segB[6];
   uint64_t desc_hi_k, desc_hi_mn;
   uint32_t kstep_mn;
   uint32_t debug_flags;

@@ -17,7 +17,7 @@ namespace asmh {
 //   blocks [nwb, ...): X role. One warp per embedding row: n_i, 1/n_i, bf16 copy, and the
 //     label -> local-class-index translation with the range check.
 // ---------------------------------------------------------------------------------------
-template <bool VEC2, bool BF16, int TX, int TY, int U>
+template <bool VEC2, int PL, int TX, int TY, int U>
 __global__ void __launch_bounds__(256) prep_kernel(Step s, const void* labels, int label_bytes,
                                                    int nwb) {
   static_assert(TX * TY == 256, "256 threads");
@@ -31,7 +31,9 @@ __global__ void __launch_bounds__(256) prep_kernel(Step s, const void* labels, i
     if (j0 < s.Cp) {
       const bool v0 = j0 < s.C, v1 = j0 + 1 < s.C;
       const float* w = s.W + j0;
+      constexpr bool BF16 = PL > 0;                 // PL: bf16 planes written (0, 1 or 3)
       __nv_bfloat16* wb = BF16 ? s.Wb + j0 : nullptr;
+      const size_t wpitch = (size_t)PL * s.Cp;
       // U rows per trip: all loads are issued before the first use so that U x 8 B per
       // thread are in flight (the bf16 stores would otherwise serialise the loads).
       for (int d0 = ty; d0 < s.D; d0 += TY * U) {
@@ -59,9 +61,17 @@ __global__ void __launch_bounds__(256) prep_kernel(Step s, const void* labels, i
           const int d = d0 + TY * u;
           a0 = fmaf(x0[u], x0[u], a0);
           a1 = fmaf(x1[u], x1[u], a1);
-          if (BF16 && d < s.D)
-            *reinterpret_cast<__nv_bfloat162*>(wb + (size_t)d * s.Cp) =
-                __floats2bfloat162_rn(x0[u], x1[u]);
+          if (BF16 && d < s.D) {
+            __nv_bfloat162* dst = reinterpret_cast<__nv_bfloat162*>(wb + (size_t)d * wpitch);
+            float r0 = x0[u], r1 = x1[u];
+#pragma unroll
+            for (int p = 0; p < PL; ++p) {             // exact split: residual after each plane
+              const __nv_bfloat162 hv = __floats2bfloat162_rn(r0, r1);
+              dst[(size_t)p * (s.Cp / 2)] = hv;
+              r0 -= __low2float(hv);
+              r1 -= __high2float(hv);
+            }
+          }
         }
       }
     }
@@ -84,7 +94,16 @@ __global__ void __launch_bounds__(256) prep_kernel(Step s, const void* labels, i
     for (int d = tx; d < s.D; d += 32) {
       const float v = __ldg(x + d);
       acc = fmaf(v, v, acc);
-      if (BF16) s.Xb[(size_t)row * s.D + d] = __float2bfloat16_rn(v);
+      if (PL > 0) {
+        __nv_bfloat16* dst = s.Xb + (size_t)row * PL * s.D + d;
+        float r = v;
+#pragma unroll
+        for (int p = 0; p < PL; ++p) {
+          const __nv_bfloat16 hv = __float2bfloat16_rn(r);
+          dst[(size_t)p * s.D] = hv;
+          r -= __bfloat162float(hv);
+        }
+      }
     }
     acc = warp_sum(acc);
     if (tx == 0) {
@@ -108,12 +127,15 @@ static void launch_prep_t(const Step& s, const void* labels, int label_bytes, cu
   const int nxb = (s.B + 7) / 8;
   const bool vec2 = (s.C % 2 == 0) && ((reinterpret_cast<uintptr_t>(s.W) & 7) == 0);
   dim3 grd(nwb + nxb);
-  if (s.mode == 1) {
-    if (vec2) prep_kernel<true, true, TX, TY, U><<<grd, 256, 0, st>>>(s, labels, label_bytes, nwb);
-    else prep_kernel<false, true, TX, TY, U><<<grd, 256, 0, st>>>(s, labels, label_bytes, nwb);
+  if (s.x3) {
+    if (vec2) prep_kernel<true, 3, TX, TY, U><<<grd, 256, 0, st>>>(s, labels, label_bytes, nwb);
+    else prep_kernel<false, 3, TX, TY, U><<<grd, 256, 0, st>>>(s, labels, label_bytes, nwb);
+  } else if (s.mode == 1) {
+    if (vec2) prep_kernel<true, 1, TX, TY, U><<<grd, 256, 0, st>>>(s, labels, label_bytes, nwb);
+    else prep_kernel<false, 1, TX, TY, U><<<grd, 256, 0, st>>>(s, labels, label_bytes, nwb);
   } else {
-    if (vec2) prep_kernel<true, false, TX, TY, U><<<grd, 256, 0, st>>>(s, labels, label_bytes, nwb);
-    else prep_kernel<false, false, TX, TY, U><<<grd, 256, 0, st>>>(s, labels, label_bytes, nwb);
+    if (vec2) prep_kernel<true, 0, TX, TY, U><<<grd, 256, 0, st>>>(s, labels, label_bytes, nwb);
+    else prep_kernel<false, 0, TX, TY, U><<<grd, 256, 0, st>>>(s, labels, label_bytes, nwb);
   }
 }
 

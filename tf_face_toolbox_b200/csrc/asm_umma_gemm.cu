@@ -50,7 +50,8 @@ constexpr float LOG2E = 1.4426950408889634f;
 // (55 vs 48 us at cfg 3): the pipeline is bound by bytes in flight (80 KB vs 192 KB), not by
 // L2 bandwidth.  Kept behind ASM_UMMA_DEBUG bit 2 as the record of that experiment.
 // U_DWOPT is the dW kernel with the classifier optimizer fused into its epilogue.
-enum { U_FWD = 0, U_BWDG = 1, U_DW = 2, U_DX = 3, U_FWDR = 4, U_DWOPT = 5 };
+// U_DWF is the dW kernel of the fp32 (x3) path: the correction term reads the fp32 weights.
+enum { U_FWD = 0, U_BWDG = 1, U_DW = 2, U_DX = 3, U_FWDR = 4, U_DWOPT = 5, U_DWF = 6 };
 
 // pipeline geometry per kernel kind
 // CG = 2: a CTA pair (cluster of 2, cta_group::2) computes one 256 x 256 tile; each CTA
@@ -117,7 +118,7 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
   constexpr bool RES = G_::RES;
   constexpr int KB = G_::KB, NST = G_::NST, A_ST = G_::A_ST, ST_B = G_::ST_B;
   constexpr int RES_B = G_::RES_B, CH_B = G_::CH_B, PIPE_B = G_::PIPE_B;
-  constexpr bool IS_DW = (KIND == U_DW || KIND == U_DWOPT);
+  constexpr bool IS_DW = (KIND == U_DW || KIND == U_DWOPT || KIND == U_DWF);
   constexpr bool A_MN = (KIND == U_BWDG || IS_DW);
   constexpr bool B_MN = (IS_FWD || IS_DW);
   constexpr bool N_FAST = (KIND == U_BWDG || IS_DW);   // tile order: n index fastest
@@ -207,7 +208,17 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
           ptx::mbar_wait(&empty[st], ph ^ 1);
           uint8_t* sA = pipe + st * ST_B;
           uint8_t* sB = sA + A_ST;
-          const int k0 = kb * KB;
+          int k0 = kb * KB, oa = 0, ob = 0;
+          if (g.nseg > 1) {
+            // x3: plane-pair segment of this K block; the plane offset goes to the INNER
+            // coordinate of each operand's tensor (K for K-major loads, M/N for MN-major)
+            const int seg = kb / g.kb_seg;
+            k0 = (kb - seg * g.kb_seg) * KB;
+            oa = g.segA[seg];
+            ob = g.segB[seg];
+          }
+          const int kA = A_MN ? k0 : k0 + oa, mA = A_MN ? m0 + oa : m0;
+          const int kB = B_MN ? k0 : k0 + ob, nB = B_MN ? n0 + ob : n0;
           if (CG == 2) {
             // both CTAs load their A rows and their half of B; all bytes are counted on the
             // leader's full barrier, which only the leader arms
@@ -215,16 +226,16 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
             if (A_MN) {
 #pragma unroll
               for (int c = 0; c < BM / 64; ++c)
-                ptx::tma_load_2d_cg2(sA + c * CH_B, &mapA, &full[st], m0 + c * 64, k0);
+                ptx::tma_load_2d_cg2(sA + c * CH_B, &mapA, &full[st], mA + c * 64, kA);
             } else {
-              ptx::tma_load_2d_cg2(sA, &mapA, &full[st], k0, m0);
+              ptx::tma_load_2d_cg2(sA, &mapA, &full[st], kA, mA);
             }
             if (B_MN) {
 #pragma unroll
               for (int c = 0; c < BN / 128; ++c)
-                ptx::tma_load_2d_cg2(sB + c * CH_B, &mapB, &full[st], n0 + (crank * 2 + c) * 64, k0);
+                ptx::tma_load_2d_cg2(sB + c * CH_B, &mapB, &full[st], nB + (crank * 2 + c) * 64, kB);
             } else {
-              ptx::tma_load_2d_cg2(sB, &mapB, &full[st], k0, n0 + crank * (BN / 2));
+              ptx::tma_load_2d_cg2(sB, &mapB, &full[st], kB, nB + crank * (BN / 2));
             }
             continue;
           }
@@ -234,16 +245,16 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
           } else if (A_MN) {
 #pragma unroll
             for (int c = 0; c < BM / 64; ++c)
-              ptx::tma_load_2d(sA + c * CH_B, &mapA, &full[st], m0 + c * 64, k0);
+              ptx::tma_load_2d(sA + c * CH_B, &mapA, &full[st], mA + c * 64, kA);
           } else {
-            ptx::tma_load_2d(sA, &mapA, &full[st], k0, m0);
+            ptx::tma_load_2d(sA, &mapA, &full[st], kA, mA);
           }
           if (B_MN) {
 #pragma unroll
             for (int c = 0; c < BN / 64; ++c)
-              ptx::tma_load_2d(sB + c * CH_B, &mapB, &full[st], n0 + c * 64, k0);
+              ptx::tma_load_2d(sB + c * CH_B, &mapB, &full[st], nB + c * 64, kB);
           } else {
-            ptx::tma_load_2d(sB, &mapB, &full[st], k0, n0);
+            ptx::tma_load_2d(sB, &mapB, &full[st], kB, nB);
           }
         }
       }
@@ -512,16 +523,24 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
               gq[b] = gp * ic;
             }
           }
-          if (leader) ptx::bulk_wait_read0();                 // previous store has drained the buffer
-          named_bar_sync(2 + half, 128);
+          // x3: G'' leaves as two bf16 planes (value, then the rounding residual), side by side
+          const int npl = s.x3 ? 2 : 1;
+#pragma unroll 1
+          for (int pl = 0; pl < npl; ++pl) {
+            if (leader) ptx::bulk_wait_read0();               // previous store has drained the buffer
+            named_bar_sync(2 + half, 128);
 #pragma unroll
-          for (int b = 0; b < 32; ++b)
-            stgh[b * 128] = __bfloat16_as_ushort(__float2bfloat16_rn(gq[b]));
-          ptx::fence_proxy_async();                           // generic writes -> async proxy
-          named_bar_sync(2 + half, 128);
-          if (leader) {
-            ptx::tma_store_2d(&mapC, stg + half * STG_HALF, m0, ib);
-            ptx::bulk_commit();
+            for (int b = 0; b < 32; ++b) {
+              const __nv_bfloat16 hv = __float2bfloat16_rn(gq[b]);
+              stgh[b * 128] = __bfloat16_as_ushort(hv);
+              if (npl > 1) gq[b] -= __bfloat162float(hv);
+            }
+            ptx::fence_proxy_async();                         // generic writes -> async proxy
+            named_bar_sync(2 + half, 128);
+            if (leader) {
+              ptx::tma_store_2d(&mapC, stg + half * STG_HALF, m0 + pl * s.Cp, ib);
+              ptx::bulk_commit();
+            }
           }
         };
         ASM_EPILOGUE_CHUNKS(process)
@@ -558,6 +577,28 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
               dst += s.C;
             }
           }
+        };
+        ASM_EPILOGUE_CHUNKS(process)
+      } else if (KIND == U_DWF) {
+        // ---- fp32 (x3) path: thread = class j, columns = d.  dW[d][j] = acc - W[d][j] q_j / c_j^2
+        // with the fp32 weights read straight from global memory (coalesced along j).
+        const int j = m0 + lane_row;
+        const bool jv = j < s.C;
+        const float coef = -(((pre0 + pre1) + (pre3 + pre4)) + pre5) * pre2 * pre2;
+        prefetch_tile(u + npairs);
+        const int d_first = n0 + col0;
+        ptx::mbar_wait(&tfull[a], aph);
+        ptx::tc_fence_after();
+        auto process = [&](const uint32_t (&r)[32], int c) {
+          const int db = d_first + c * 32;
+          if (!jv || db >= s.D) return;
+          const size_t base = (size_t)db * s.C + j;
+          float w[32];
+#pragma unroll
+          for (int b = 0; b < 32; ++b) w[b] = __ldg(s.W + base + (size_t)b * s.C);
+#pragma unroll
+          for (int b = 0; b < 32; ++b)
+            s.dW[base + (size_t)b * s.C] = fmaf(w[b], coef, __uint_as_float(r[b]));
         };
         ASM_EPILOGUE_CHUNKS(process)
       } else if (KIND == U_DWOPT) {
@@ -701,22 +742,59 @@ int umma_dx_splits(int B, int D, int Cp, int num_sms, int cg) {
 
 bool umma_build_maps(UmmaMaps* m, const Step& s) {
   bool ok = true;
-  // Xb [B, D]
-  ok &= encode_map(&m->xb_k, s.Xb, s.D, s.B, s.D, 64, 128);     // A of FWD  (K-major, M = batch)
-  ok &= encode_map(&m->xb_k256, s.Xb, s.D, s.B, s.D, 64, 256);  // B of BWDG (K-major, N = batch)
-  ok &= encode_map(&m->xb_mn, s.Xb, s.D, s.B, s.D, 64, 64);     // B of DW   (MN-major, N = d)
-  // Wb [D, Cp]
-  ok &= encode_map(&m->wb_mn, s.Wb, s.Cp, s.D, s.Cp, 64, 64);   // B of FWD / A of BWDG (MN-major)
-  ok &= encode_map(&m->wb_mn32, s.Wb, s.Cp, s.D, s.Cp, 64, 32); // B of FWDR (32-deep K stages)
-  ok &= encode_map(&m->wb_k, s.Wb, s.Cp, s.D, s.Cp, 64, 256);   // B of DX   (K-major, N = d)
-  ok &= encode_map(&m->wb_k128, s.Wb, s.Cp, s.D, s.Cp, 64, 128);  // B half of DX in a CTA pair
-  // G'' [B, Cp]
-  ok &= encode_map(&m->g_k, s.G, s.Cp, s.B, s.Cp, 64, 128);     // A of DX   (K-major, M = batch)
-  ok &= encode_map(&m->g_mn, s.G, s.Cp, s.B, s.Cp, 64, 64);     // A of DW   (MN-major, M = class)
-  ok &= encode_map(&m->g_st, s.G, s.Cp, s.B, s.Cp, 128, 32, false);  // BWDG store (no swizzle)
-  ok &= encode_map(&m->wb_box, s.Wb, s.Cp, s.D, s.Cp, 128, 32, false);  // DW weight chunks
+  // x3: the bf16 planes of each operand lie side by side along the inner dimension
+  const uint64_t xd = (uint64_t)(s.x3 ? 3 : 1) * s.D;      // Xb [B, D] or [B, 3D]
+  const uint64_t wc = (uint64_t)(s.x3 ? 3 : 1) * s.Cp;     // Wb [D, Cp] or [D, 3Cp]
+  const uint64_t gc = (uint64_t)(s.x3 ? 2 : 1) * s.Cp;     // G'' [B, Cp] or [B, 2Cp]
+  ok &= encode_map(&m->xb_k, s.Xb, xd, s.B, xd, 64, 128);     // A of FWD  (K-major, M = batch)
+  ok &= encode_map(&m->xb_k256, s.Xb, xd, s.B, xd, 64, 256);  // B of BWDG (K-major, N = batch)
+  ok &= encode_map(&m->xb_mn, s.Xb, xd, s.B, xd, 64, 64);     // B of DW   (MN-major, N = d)
+  ok &= encode_map(&m->wb_mn, s.Wb, wc, s.D, wc, 64, 64);     // B of FWD / A of BWDG (MN-major)
+  ok &= encode_map(&m->wb_mn32, s.Wb, wc, s.D, wc, 64, 32);   // B of FWDR (32-deep K stages)
+  ok &= encode_map(&m->wb_k, s.Wb, wc, s.D, wc, 64, 256);     // B of DX   (K-major, N = d)
+  ok &= encode_map(&m->wb_k128, s.Wb, wc, s.D, wc, 64, 128);  // B half of DX in a CTA pair
+  ok &= encode_map(&m->g_k, s.G, gc, s.B, gc, 64, 128);       // A of DX   (K-major, M = batch)
+  ok &= encode_map(&m->g_mn, s.G, gc, s.B, gc, 64, 64);       // A of DW   (MN-major, M = class)
+  ok &= encode_map(&m->g_st, s.G, gc, s.B, gc, 128, 32, false);    // BWDG store (no swizzle)
+  ok &= encode_map(&m->wb_box, s.Wb, wc, s.D, wc, 128, 32, false); // DW weight chunks
   return ok;
 }
+
+// x3 segment tables.  A contraction of two fp32 operands split as a = a0 + a1 + a2 (bf16
+// planes, |a_p| <= 2^-8p |a|) keeps the plane pairs with p + q <= 2: what is dropped is below
+// 2^-24 relative, the fp32 rounding level.  G'' carries two planes (its own error budget is the
+// 2e-3 / cosine bar on gradients; 2^-16 is far inside it).  Segments are accumulated smallest
+// term first.
+static int x3_segments() {
+  static int n = -1;
+  if (n < 0) {
+    const char* e = getenv("ASM_X3_SEGS");     // 3: (0,0),(0,1),(1,0) only (~2^-16)
+    n = e ? atoi(e) : 6;
+    if (n < 1) n = 1;
+    if (n > 6) n = 6;
+  }
+  return n;
+}
+// pa/pb: plane of operand A / B per segment; strideA/strideB: elements per plane
+static void set_segments(UmmaArgs& g, bool on, int kb_seg, const int* pa, const int* pb, int n,
+                         int strideA, int strideB) {
+  g.kb_seg = kb_seg;
+  g.nseg = 1;
+  g.segA[0] = g.segB[0] = 0;
+  if (on) {
+    g.nseg = n;
+    for (int i = 0; i < n; ++i) {             // reversed: small terms first
+      g.segA[i] = pa[n - 1 - i] * strideA;
+      g.segB[i] = pb[n - 1 - i] * strideB;
+    }
+  }
+  g.kb_total = g.nseg * kb_seg;
+  g.kb_per = g.kb_total;
+}
+static const int kSegHi[6] = {0, 0, 1, 1, 0, 2};   // three-plane operand pairs: (x, w)
+static const int kSegLo[6] = {0, 1, 0, 1, 2, 0};
+static const int kSegG[5] = {0, 0, 1, 1, 0};       // two-plane G'' against a three-plane operand
+static const int kSegO[5] = {0, 1, 0, 1, 2};
 
 static UmmaArgs base_args(const UmmaTuning& tu) {
   UmmaArgs g{};
@@ -740,7 +818,7 @@ void launch_k(int units, const CUtensorMap& a, const CUtensorMap& b, const CUten
               const Step& s, const UmmaArgs& g, cudaStream_t st) {
   if (units <= 0) return;
   // DW follows an event record (the dX fork), everything else follows a kernel directly
-  const bool pdl = s.pdl != 0 && KIND != U_DW && KIND != U_DWOPT;
+  const bool pdl = s.pdl != 0 && KIND != U_DW && KIND != U_DWOPT && KIND != U_DWF;
   launch_pdl(umma_kernel<KIND, CG>, dim3(units * CG), dim3(NUM_THREADS), Geo<KIND, CG>::SMEM, st, pdl,
              CG, a, b, c, s, g);
 }
@@ -757,6 +835,8 @@ cudaError_t umma_configure() {
   if ((e = set_smem<U_DW, 2>()) != cudaSuccess) return e;
   if ((e = set_smem<U_DWOPT, 1>()) != cudaSuccess) return e;
   if ((e = set_smem<U_DWOPT, 2>()) != cudaSuccess) return e;
+  if ((e = set_smem<U_DWF, 1>()) != cudaSuccess) return e;
+  if ((e = set_smem<U_DWF, 2>()) != cudaSuccess) return e;
   if ((e = set_smem<U_DX, 1>()) != cudaSuccess) return e;
   return set_smem<U_DX, 2>();
 }
@@ -768,7 +848,7 @@ void launch_umma_forward(const Step& s, const UmmaMaps& m, const UmmaTuning& tu,
   g.mt = ((s.B + BM - 1) / BM + cg - 1) / cg;
   g.nt = s.Cp / BN;
   const int units = umma_forward_grid(s.B, s.Cp, num_sms, cg) / cg;
-  if (s.D <= 512 && (tu.debug_flags & 4) && cg == 1) {   // opt-in: measured slower (55 vs 48 us)
+  if (s.D <= 512 && (tu.debug_flags & 4) && cg == 1 && !s.x3) {   // opt-in: measured slower (55 vs 48 us)
     // Xb row tile resident in shared memory, weights stream in 32-deep K stages
     g.kb_total = (s.D + 31) / 32;
     g.kb_per = g.kb_total;
@@ -776,8 +856,7 @@ void launch_umma_forward(const Step& s, const UmmaMaps& m, const UmmaTuning& tu,
     launch_k<U_FWDR, 1>(units, m.xb_k, m.wb_mn32, m.wb_mn32, s, g, st);
     return;
   }
-  g.kb_total = (s.D + BK - 1) / BK;
-  g.kb_per = g.kb_total;
+  set_segments(g, s.x3 != 0, (s.D + BK - 1) / BK, kSegHi, kSegLo, x3_segments(), s.D, s.Cp);
   if (cg == 2) launch_k<U_FWD, 2>(units, m.xb_k, m.wb_mn, m.wb_mn, s, g, st);
   else launch_k<U_FWD, 1>(units, m.xb_k, m.wb_mn, m.wb_mn, s, g, st);
 }
@@ -788,8 +867,8 @@ void launch_umma_bwdg(const Step& s, const UmmaMaps& m, const UmmaTuning& tu, in
   const int cg = (tu.cg_mask & 2) ? 2 : 1;
   g.mt = s.Cp / (BM * cg);
   g.nt = (s.B + BN - 1) / BN;
-  g.kb_total = (s.D + BK - 1) / BK;
-  g.kb_per = g.kb_total;
+  // A = weights, B = embeddings: the same plane pairs with the roles swapped
+  set_segments(g, s.x3 != 0, (s.D + BK - 1) / BK, kSegLo, kSegHi, x3_segments(), s.Cp, s.D);
   const int units = min(g.mt * g.nt, num_sms / cg);
   if (cg == 2) launch_k<U_BWDG, 2>(units, m.wb_mn, m.xb_k, m.g_st, s, g, st);
   else launch_k<U_BWDG, 1>(units, m.wb_mn, m.xb_k256, m.g_st, s, g, st);
@@ -801,9 +880,14 @@ void launch_umma_dw(const Step& s, const UmmaMaps& m, const UmmaTuning& tu, int 
   const int cg = (tu.cg_mask & 4) ? 2 : 1;
   g.mt = s.Cp / (BM * cg);
   g.nt = (s.D + BN - 1) / BN;
-  g.kb_total = (s.B + BK - 1) / BK;
-  g.kb_per = g.kb_total;
+  set_segments(g, s.x3 != 0, (s.B + BK - 1) / BK, kSegG, kSegO, x3_segments() < 5 ? x3_segments() : 5,
+               s.Cp, s.D);
   const int units = min(g.mt * g.nt, num_sms / cg);
+  if (s.opt.kind == 0 && s.x3) {
+    if (cg == 2) launch_k<U_DWF, 2>(units, m.g_mn, m.xb_mn, m.wb_box, s, g, st);
+    else launch_k<U_DWF, 1>(units, m.g_mn, m.xb_mn, m.wb_box, s, g, st);
+    return;
+  }
   if (s.opt.kind != 0) {
     if (cg == 2) launch_k<U_DWOPT, 2>(units, m.g_mn, m.xb_mn, m.wb_box, s, g, st);
     else launch_k<U_DWOPT, 1>(units, m.g_mn, m.xb_mn, m.wb_box, s, g, st);
@@ -819,7 +903,8 @@ void launch_umma_dx(const Step& s, const UmmaMaps& m, const UmmaTuning& tu, int 
   const int cg = fwd_cg(s.B, (tu.cg_mask & 8) ? 2 : 1);
   g.mt = ((s.B + BM - 1) / BM + cg - 1) / cg;
   g.nt = (s.D + BN - 1) / BN;
-  g.kb_total = (s.Cp + BK - 1) / BK;
+  set_segments(g, s.x3 != 0, (s.Cp + BK - 1) / BK, kSegG, kSegO, x3_segments() < 5 ? x3_segments() : 5,
+               s.Cp, s.Cp);
   g.ks = s.KS;
   g.kb_per = (g.kb_total + g.ks - 1) / g.ks;
   const int units = min(g.mt * g.nt * g.ks, num_sms / cg);
