@@ -74,6 +74,21 @@ def _worker(rank, world, port, B, D, C, q):
         b = B // world
         loss, dX_local, dW_local = head.step(inp.X[rank * b:(rank + 1) * b], inp.y[rank * b:(rank + 1) * b], 5.0)
         Wfull = head.gather_weights()
+        # checkpoint round trip in the reference's layout / naming (saver.py:36-40, 62-72)
+        sd = head.state_dict()
+        assert list(sd.keys()) == ["classifier/fc_classifier/weights"]
+        ptr = head.weights.data_ptr()
+        head.load_state_dict({"replicated_0/classifier/fc_classifier/weights": sd[head.VARIABLE_NAME] * 2.0,
+                              "replicated_1/classifier/fc_classifier/weights": sd[head.VARIABLE_NAME] * 3.0})
+        assert head.weights.data_ptr() == ptr                      # in place
+        assert torch.equal(head.weights, inp.W[:, lo:hi] * 2.0)    # tower 0 wins
+        head.load_state_dict(sd)
+        assert torch.equal(head.weights, inp.W[:, lo:hi])
+        try:
+            head.load_state_dict({"backbone/conv1/weights": torch.zeros(1)})
+            raise AssertionError("missing classifier variable must raise")
+        except KeyError:
+            pass
         q.put((rank, float(loss), dX_local.numpy(), dW_local.numpy(), lo, hi, Wfull.numpy()))
     finally:
         dist.destroy_process_group()

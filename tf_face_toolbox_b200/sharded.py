@@ -252,3 +252,33 @@ class ShardedASoftmaxHead:
         pad[:, : self.hi - self.lo] = self.weights
         allw = self._all_gather(pad)                                     # [G, D, per]
         return allw.permute(1, 0, 2).reshape(self.D, -1)[:, : self.C].contiguous()
+
+    # ---- checkpoint layout (saver.py:30-80) ------------------------------------------------
+    VARIABLE_NAME = "classifier/fc_classifier/weights"      # nets/sphere.py:84-90
+
+    def state_dict(self) -> dict:
+        """What DataParallelSaverBuilder.save_op writes for the classifier: ONE [D, C] fp32
+        tensor under the variable name with the tower prefix (`replicated_<k>/`) stripped
+        (saver.py:36-40).  Collective: every rank must call it; every rank gets the full tensor."""
+        return {self.VARIABLE_NAME: self.gather_weights()}
+
+    def load_weights(self, weights_full: torch.Tensor) -> None:
+        """Inverse of gather_weights(): keep this rank's class slice of a [D, C] tensor.  The
+        shard is overwritten in place, so captured CUDA graphs keep pointing at it."""
+        if tuple(weights_full.shape) != (self.D, self.C):
+            raise ValueError(f"expected weights [{self.D}, {self.C}], got {tuple(weights_full.shape)}")
+        self.weights.copy_(weights_full[:, self.lo:self.hi].to(torch.float32))
+
+    def load_state_dict(self, state: dict) -> None:
+        """Restore from a reference-format checkpoint dict.  Accepts the stripped name or any
+        `replicated_<k>/...` spelling of it (restore_op strips the first path component for
+        tower variables, saver.py:62-72); tower 0 wins if several are present."""
+        found = None
+        for name in sorted(state.keys()):
+            base = "/".join(name.split("/")[1:]) if name.startswith("replicated_") else name
+            if base == self.VARIABLE_NAME:
+                found = state[name]
+                break
+        if found is None:
+            raise KeyError(f"no '{self.VARIABLE_NAME}' (or replicated_<k>/ variant) in checkpoint")
+        self.load_weights(torch.as_tensor(found))
