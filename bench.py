@@ -327,6 +327,20 @@ def run_ours(args, cfg):
     ms_step = value_ms[value_path]
     value = B / (ms_step * 1e-3)
 
+    # per-step distribution of the chosen path (SURVEY 8d asks for median and p10/p90): one
+    # event between consecutive steps; the headline stays the K-step mean above
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
+    barrier()
+    for i in range(K):
+        evs[i].record()
+        if flush is not None:
+            flush.zero_()
+        run_step()
+    evs[K].record()
+    barrier()
+    per = sorted(evs[i].elapsed_time(evs[i + 1]) - flush_ms for i in range(K))
+    step_dist = {"p10": per[int(0.1 * (K - 1))], "p50": per[(K - 1) // 2], "p90": per[int(round(0.9 * (K - 1)))],
+                 "note": "rank-0 CUDA-event time of single steps, same loop as value"}
     note("value loop done: %.4f ms/step" % ms_step)
     # ---- (2) per-kernel durations (CUDA events on the launching stream, inside the library)
     kernels = {}
@@ -452,7 +466,7 @@ def run_ours(args, cfg):
         dom = max((k for k in roof_kernels if "bound" in k), key=lambda k: k["ms"], default=None)
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic_cfg3.json")
-        if world == 1 and args.workload == "cfg3" and os.path.exists(tpath):
+        if world == 1 and args.workload == "cfg3" and mode == "bf16" and os.path.exists(tpath):
             traffic = json.load(open(tpath)).get("kernels", {})
         roofline = None
         if dom is not None:
@@ -473,6 +487,7 @@ def run_ours(args, cfg):
                     "h2d_bytes_per_step": int(b_local * D * 4 + b_local * 4), "d2h_bytes_per_step": 4},
             "gpu_launches": launches_per_step * K,
             "cuda_graph": graphed is not None, "value_path": value_path, "ms_per_step_by_path": value_ms,
+            "ms_per_step_dist": step_dist,
             "roofline": roofline,
             "step_tensor_frac": step_flops / (ms_step * 1e-3) / 1e12 / peaks["tf_burst"],
             "step_algorithmic_tflops": step_flops / (ms_step * 1e-3) / 1e12,

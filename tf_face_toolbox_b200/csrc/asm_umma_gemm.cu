@@ -51,24 +51,30 @@ constexpr float LOG2E = 1.4426950408889634f;
 // L2 bandwidth.  Kept behind ASM_UMMA_DEBUG bit 2 as the record of that experiment.
 // U_DWOPT is the dW kernel with the classifier optimizer fused into its epilogue.
 // U_DWF is the dW kernel of the fp32 (x3) path: the correction term reads the fp32 weights.
-enum { U_FWD = 0, U_BWDG = 1, U_DW = 2, U_DX = 3, U_FWDR = 4, U_DWOPT = 5, U_DWF = 6 };
+// U_BWDG1 is BWDG with the earlier geometry (6 operand stages, one staging buffer, two named
+// barriers per chunk), selectable with ASM_UMMA_DEBUG bit 3 for same-box A/B timing.
+enum { U_FWD = 0, U_BWDG = 1, U_DW = 2, U_DX = 3, U_FWDR = 4, U_DWOPT = 5, U_DWF = 6, U_BWDG1 = 7 };
 
 // pipeline geometry per kernel kind
 // CG = 2: a CTA pair (cluster of 2, cta_group::2) computes one 256 x 256 tile; each CTA
 // stages its own 128 A rows and HALF of the B tile, so a stage is 32 KB and the ring is 6 deep.
 template <int KIND, int CG = 1> struct Geo {
   static constexpr bool RES = (KIND == U_FWDR);
-  static constexpr int KB = RES ? 32 : BK;                 // K elements per pipeline stage
+  static constexpr int KB = (RES && CG == 1) ? 32 : BK;    // K elements per pipeline stage
   // the dW kernel of a CTA pair trades its 6th operand stage for a 4-deep weight-chunk ring
   static constexpr int NWB = (KIND == U_DW && CG == 2) ? 4 : 2;  // weight-chunk buffers per column half
-  static constexpr int NST = RES ? 5 : (CG == 2 ? ((KIND == U_DW) ? 5 : 6) : STAGES);   // pipeline depth
+  // the BWDG kernel of a CTA pair trades its 6th operand stage for double-buffered G'' staging
+  static constexpr int NSB = (KIND == U_BWDG && CG == 2) ? 2 : 1;   // G'' staging buffers per column half
+  static constexpr int NST = RES ? 5 : (CG == 2 ? ((KIND == U_DW || KIND == U_BWDG) ? 5 : 6) : STAGES);   // pipeline depth
   static constexpr int A_ST = RES ? 0 : BM * KB * 2;       // A bytes per stage
   static constexpr int B_ST = BN * KB * 2 / CG;            // B bytes per stage (per CTA)
   static constexpr int ST_B = A_ST + B_ST;
   static constexpr int RES_B = RES ? 8 * A_BYTES : 0;      // resident A block (K <= 512)
   static constexpr int CH_B = 64 * KB * 2;                 // one 64-wide MN-major chunk
   static constexpr int PIPE_B = RES_B + NST * ST_B;
-  static constexpr int AUX_R = RES ? AUX_VEC : (KIND == U_DW ? 2 * NWB * WB_BUF : AUX_REGION);
+  static constexpr int AUX_R = RES ? AUX_VEC
+                               : (KIND == U_DW ? 2 * NWB * WB_BUF
+                                               : (NSB == 2 ? AUX_VEC + 2 * AUX_STG : AUX_REGION));
   static constexpr int SMEM = PIPE_B + AUX_BARS + AUX_R + 1024;
   static_assert(SMEM <= 232448, "exceeds the 227 KB shared memory of an sm_100 CTA");
 };
@@ -109,7 +115,6 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
             const __grid_constant__ CUtensorMap mapC, Step s, UmmaArgs g) {
   using G_ = Geo<KIND, CG>;
   pdl_trigger();      // the next kernel's CTAs may take over SMs as this grid's tail drains
-  static_assert(CG == 1 || KIND != U_FWDR, "the resident forward is single-CTA");
   // CTA pair: rank within the cluster, work is distributed over PAIRS
   const int crank = CG == 2 ? (int)ptx::cluster_ctarank() : 0;
   const int pair_id = (int)blockIdx.x / CG;
@@ -119,9 +124,10 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
   constexpr int KB = G_::KB, NST = G_::NST, A_ST = G_::A_ST, ST_B = G_::ST_B;
   constexpr int RES_B = G_::RES_B, CH_B = G_::CH_B, PIPE_B = G_::PIPE_B;
   constexpr bool IS_DW = (KIND == U_DW || KIND == U_DWOPT || KIND == U_DWF);
-  constexpr bool A_MN = (KIND == U_BWDG || IS_DW);
+  constexpr bool IS_BWDG = (KIND == U_BWDG || KIND == U_BWDG1);
+  constexpr bool A_MN = (IS_BWDG || IS_DW);
   constexpr bool B_MN = (IS_FWD || IS_DW);
-  constexpr bool N_FAST = (KIND == U_BWDG || IS_DW);   // tile order: n index fastest
+  constexpr bool N_FAST = (IS_BWDG || IS_DW);   // tile order: n index fastest
   extern __shared__ uint8_t smem_raw[];
   // align to 1024 B (SWIZZLE_128B atoms) by adding an integer offset, so that the compiler
   // keeps the shared address space (ld.shared, not generic loads) for everything below
@@ -138,7 +144,8 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
   float* vec0 = reinterpret_cast<float*>(smem + PIPE_B + AUX_BARS);   // [2][BN]
   float* vec1 = vec0 + 2 * BN;
   float* vec2 = vec1 + 2 * BN;
-  uint8_t* stg = smem + PIPE_B + AUX_BARS + AUX_VEC;                  // BWDG: [2][STG_HALF]
+  uint8_t* stg = smem + PIPE_B + AUX_BARS + AUX_VEC;                  // BWDG: [2 halves][NSB][STG_HALF]
+  constexpr int NSB = G_::NSB;
   uint8_t* wbuf = smem + PIPE_B + AUX_BARS;                           // DW: [2][2][WB_BUF]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -146,7 +153,7 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
   if (warp == 0 && ptx::elect_one()) {
     ptx::prefetch_tmap(&mapA);
     ptx::prefetch_tmap(&mapB);
-    if (KIND == U_BWDG || KIND == U_DW) ptx::prefetch_tmap(&mapC);
+    if (IS_BWDG || KIND == U_DW) ptx::prefetch_tmap(&mapC);
   }
   if (warp == 1 && ptx::elect_one()) {
     for (int i = 0; i < NST; ++i) {
@@ -192,10 +199,17 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
       if (RES && pair_id < total) {
         // the CTA's 128 batch rows of Xb, all of K, loaded once (grid % mt == 0)
         const int nblk = (s.D + 63) / 64;
-        ptx::mbar_expect_tx(&wfull[0], nblk * A_BYTES);
-        for (int i = 0; i < nblk; ++i)
-          ptx::tma_load_2d(smem + i * A_BYTES, &mapA, &wfull[0], i * 64,
-                           ((int)blockIdx.x % g.mt) * BM);
+        const int mrow = ((pair_id % g.mt) * CG + crank) * BM;
+        if (CG == 2) {
+          // both CTAs' blocks are counted on the leader's barrier (the leader issues the MMAs)
+          if (crank == 0) ptx::mbar_expect_tx(&wfull[0], 2 * nblk * A_BYTES);
+          for (int i = 0; i < nblk; ++i)
+            ptx::tma_load_2d_cg2(smem + i * A_BYTES, &mapA, &wfull[0], i * 64, mrow);
+        } else {
+          ptx::mbar_expect_tx(&wfull[0], nblk * A_BYTES);
+          for (int i = 0; i < nblk; ++i)
+            ptx::tma_load_2d(smem + i * A_BYTES, &mapA, &wfull[0], i * 64, mrow);
+        }
       }
       for (int u = pair_id; u < total; u += npairs) {
         int z, m_idx, n_idx;
@@ -223,7 +237,9 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
             // both CTAs load their A rows and their half of B; all bytes are counted on the
             // leader's full barrier, which only the leader arms
             if (crank == 0) ptx::mbar_expect_tx(&full[st], 2 * ST_B);
-            if (A_MN) {
+            if (RES) {
+              // A is resident
+            } else if (A_MN) {
 #pragma unroll
               for (int c = 0; c < BM / 64; ++c)
                 ptx::tma_load_2d_cg2(sA + c * CH_B, &mapA, &full[st], mA + c * 64, kA);
@@ -282,7 +298,7 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
           ptx::mbar_wait(&full[st], ph);
           ptx::tc_fence_after();
           // resident A: 64-wide K blocks of 16 KB; stage kb covers K = [32 kb, 32 kb + 32)
-          const uint32_t aA = RES ? ptx::smem_u32(smem + (kb >> 1) * A_BYTES) + (kb & 1) * 64u
+          const uint32_t aA = RES ? ptx::smem_u32(smem + ((kb * KB) >> 6) * A_BYTES) + ((kb * KB) & 63) * 2u
                                   : ptx::smem_u32(pipe + st * ST_B);
           const uint32_t aB = ptx::smem_u32(pipe + st * ST_B) + A_ST;
 #pragma unroll
@@ -347,7 +363,7 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
       decode(pu, pz, pm, pn);
       pm = pm * CG + crank;
       if (IS_FWD) pre0 = s.inv_c[pn * BN + et];
-      if (KIND == U_BWDG) {
+      if (IS_BWDG) {
         const int i = pn * BN + et;
         const bool iv = i < s.B;
         pre0 = iv ? s.negoff[i] : -INFINITY;                  // -(lse_i log2e) + log2(1/B)
@@ -485,7 +501,7 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
           }
         };
         ASM_EPILOGUE_CHUNKS(process)
-      } else if (KIND == U_BWDG) {
+      } else if (IS_BWDG) {
         // ---- thread = class j (row m), columns = batch rows i.  Stage the per-row terms.
         v0[et] = pre0;
         v1[et] = pre1;
@@ -497,7 +513,10 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
         // G'' leaves through shared memory: the four warps of a column half stage a
         // [32 rows x 128 classes] bf16 block and one thread issues a TMA store (rows >= B are
         // clipped by the hardware), so the hot loop has no global address arithmetic at all.
-        unsigned short* stgh = reinterpret_cast<unsigned short*>(stg + half * STG_HALF) + lane_row;
+        // With two staging buffers per half (CTA pairs) a chunk costs ONE named barrier: the
+        // leader confirms, before the barrier of chunk c, that the store of chunk c-1 has
+        // drained its buffer -- the buffer chunk c+1 writes after that barrier.
+        uint8_t* stg_half = stg + half * NSB * STG_HALF;
         const bool leader = (threadIdx.x == 128 + half * 128);
         named_bar_sync(1, EPI_THREADS);
         ptx::mbar_wait(&tfull[a], aph);
@@ -527,8 +546,10 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
           const int npl = s.x3 ? 2 : 1;
 #pragma unroll 1
           for (int pl = 0; pl < npl; ++pl) {
-            if (leader) ptx::bulk_wait_read0();               // previous store has drained the buffer
-            named_bar_sync(2 + half, 128);
+            uint8_t* sbuf = stg_half + (NSB == 2 ? ((c * npl + pl) & 1) * STG_HALF : 0);
+            unsigned short* stgh = reinterpret_cast<unsigned short*>(sbuf) + lane_row;
+            if (leader) ptx::bulk_wait_read0();               // earlier stores have drained their buffers
+            if (NSB == 1) named_bar_sync(2 + half, 128);
 #pragma unroll
             for (int b = 0; b < 32; ++b) {
               const __nv_bfloat16 hv = __float2bfloat16_rn(gq[b]);
@@ -538,7 +559,7 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
             ptx::fence_proxy_async();                         // generic writes -> async proxy
             named_bar_sync(2 + half, 128);
             if (leader) {
-              ptx::tma_store_2d(&mapC, stg + half * STG_HALF, m0 + pl * s.Cp, ib);
+              ptx::tma_store_2d(&mapC, sbuf, m0 + pl * s.Cp, ib);
               ptx::bulk_commit();
             }
           }
@@ -660,7 +681,7 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
       s.part[(size_t)fwd_row * s.NT + (pair_id / g.mt) * 2 + half] = make_float2(run_m, run_z);
   }
 
-  if (KIND == U_BWDG && (threadIdx.x == 128 || threadIdx.x == 256)) ptx::bulk_wait0();
+  if (IS_BWDG && (threadIdx.x == 128 || threadIdx.x == 256)) ptx::bulk_wait0();
   ptx::tc_fence_before();
   __syncthreads();
   if (CG == 2) ptx::cluster_sync_all();       // the peer may still be read / signalled by the leader
@@ -829,8 +850,10 @@ cudaError_t umma_configure() {
   if ((e = set_smem<U_FWD, 1>()) != cudaSuccess) return e;
   if ((e = set_smem<U_FWD, 2>()) != cudaSuccess) return e;
   if ((e = set_smem<U_FWDR, 1>()) != cudaSuccess) return e;
+  if ((e = set_smem<U_FWDR, 2>()) != cudaSuccess) return e;
   if ((e = set_smem<U_BWDG, 1>()) != cudaSuccess) return e;
   if ((e = set_smem<U_BWDG, 2>()) != cudaSuccess) return e;
+  if ((e = set_smem<U_BWDG1, 2>()) != cudaSuccess) return e;
   if ((e = set_smem<U_DW, 1>()) != cudaSuccess) return e;
   if ((e = set_smem<U_DW, 2>()) != cudaSuccess) return e;
   if ((e = set_smem<U_DWOPT, 1>()) != cudaSuccess) return e;
@@ -848,6 +871,13 @@ void launch_umma_forward(const Step& s, const UmmaMaps& m, const UmmaTuning& tu,
   g.mt = ((s.B + BM - 1) / BM + cg - 1) / cg;
   g.nt = s.Cp / BN;
   const int units = umma_forward_grid(s.B, s.Cp, num_sms, cg) / cg;
+  if (s.D <= 512 && (tu.debug_flags & 4) && cg == 2 && !s.x3) {
+    // opt-in: Xb row tiles resident in both CTAs of a pair, only the weight halves stream
+    g.kb_total = (s.D + BK - 1) / BK;
+    g.kb_per = g.kb_total;
+    launch_k<U_FWDR, 2>(units, m.xb_k, m.wb_mn, m.wb_mn, s, g, st);
+    return;
+  }
   if (s.D <= 512 && (tu.debug_flags & 4) && cg == 1 && !s.x3) {   // opt-in: measured slower (55 vs 48 us)
     // Xb row tile resident in shared memory, weights stream in 32-deep K stages
     g.kb_total = (s.D + 31) / 32;
@@ -870,7 +900,8 @@ void launch_umma_bwdg(const Step& s, const UmmaMaps& m, const UmmaTuning& tu, in
   // A = weights, B = embeddings: the same plane pairs with the roles swapped
   set_segments(g, s.x3 != 0, (s.D + BK - 1) / BK, kSegLo, kSegHi, x3_segments(), s.Cp, s.D);
   const int units = min(g.mt * g.nt, num_sms / cg);
-  if (cg == 2) launch_k<U_BWDG, 2>(units, m.wb_mn, m.xb_k, m.g_st, s, g, st);
+  if (cg == 2 && (tu.debug_flags & 8)) launch_k<U_BWDG1, 2>(units, m.wb_mn, m.xb_k, m.g_st, s, g, st);
+  else if (cg == 2) launch_k<U_BWDG, 2>(units, m.wb_mn, m.xb_k, m.g_st, s, g, st);
   else launch_k<U_BWDG, 1>(units, m.wb_mn, m.xb_k256, m.g_st, s, g, st);
 }
 
