@@ -632,10 +632,45 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
         prefetch_tile(u + npairs);
         const int d_first = n0 + col0;
         const OptParams op = s.opt;
+        // The weights and optimizer state are read with plain (register) loads, 16 columns at
+        // a time, which alone cannot keep enough bytes in flight to HBM.  So the 128 threads of
+        // a column half pull the NEXT 32-column chunk of W / state into L2 (one prefetch per
+        // 128-byte line) before working on the current one: the loads that follow hit L2.
+        const int ht = et & 127;
+        auto prefetch_chunk = [&](int pm0, int pdb) {
+          if (g.debug_flags & 16) return;                      // A/B knob: no prefetch
+          // [32 d x 128 classes] fp32 per array: 4 lines per row (+1 when the row is not
+          // line-aligned, covered by the first 32 threads)
+          const int row = ht >> 2;
+          if (pdb + row < s.D) {
+            const size_t e0 = (size_t)(pdb + row) * s.C + pm0 + (ht & 3) * 32;
+            if (pm0 + (ht & 3) * 32 < s.C) {
+              ptx::prefetch_l2(s.Wmut + e0);
+              ptx::prefetch_l2(s.opt_s0 + e0);
+              if (op.kind == 2) ptx::prefetch_l2(s.opt_s1 + e0);
+            }
+          }
+          if (ht < 32 && pdb + ht < s.D && pm0 + 127 < s.C) {
+            const size_t e1 = (size_t)(pdb + ht) * s.C + pm0 + 127;
+            ptx::prefetch_l2(s.Wmut + e1);
+            ptx::prefetch_l2(s.opt_s0 + e1);
+            if (op.kind == 2) ptx::prefetch_l2(s.opt_s1 + e1);
+          }
+        };
+        if (lt == 0) prefetch_chunk(m0, d_first);
+        int nm0 = -1, nd_first = 0;                           // first chunk of this CTA's next tile
+        if (u + npairs < total) {
+          int nz, nmi, nni;
+          decode(u + npairs, nz, nmi, nni);
+          nm0 = (nmi * CG + crank) * BM;
+          nd_first = nni * BN + col0;
+        }
         ptx::mbar_wait(&tfull[a], aph);
         ptx::tc_fence_after();
         auto process = [&](const uint32_t (&r)[32], int c) {
           const int db = d_first + c * 32;
+          if (c < 3) prefetch_chunk(m0, db + 32);
+          else if (nm0 >= 0) prefetch_chunk(nm0, nd_first);
           if (!jv || db >= s.D) return;
 #pragma unroll
           for (int hf = 0; hf < 2; ++hf) {                   // 16 columns at a time
