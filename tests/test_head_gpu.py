@@ -70,6 +70,15 @@ def test_fp32_small_shapes_all_margins(B, D, C, m):
     check_against_oracle(inp, m, 5.0, "fp32", logits=True)
 
 
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("B,D,C", [(1, 64, 300), (32, 64, 5), (256, 1024, 2000), (64, 2048, 1500), (700, 256, 1300)])
+def test_edge_shapes_on_the_tensor_core_kernels(B, D, C, mode):
+    """One row, fewer classes than a tile, wide embeddings (the reference's ResNeXt emits
+    D = 2048, nets/resnext.py), a batch that is not a multiple of the 128-row tile."""
+    inp = make_inputs(B, D, C, seed=77)
+    check_against_oracle(inp, 4, 5.0, mode)
+
+
 @pytest.mark.parametrize("lam", [0.0, 5.0, 1000 / 1.12])
 def test_fp32_lambda_values(lam):
     inp = make_inputs(64, 128, 3000, seed=5)
