@@ -7,6 +7,7 @@
 #include <string.h>
 
 #include <new>
+#include <vector>
 
 #include "../../include/asoftmax_b200.h"
 #include "asm_kernels.cuh"
@@ -25,6 +26,7 @@ struct asm_head {
   size_t dx_part_capacity = 0;   // floats
   UmmaMaps maps{};
   int maps_B = -1;
+  bool defer_loss = true;        // ASM_DEFER_LOSS=0: combine reduces the loss itself (A/B knob)
   bool tc = false;               // tcgen05 kernels (bf16 mode, or fp32 mode through bf16 planes)
   UmmaTuning tune{8192, 1024, 2048, 15, 0};   // CTA pairs on all four kernels (ASM_UMMA_CG=0: single-CTA)
   bool fwd_valid = false;
@@ -200,7 +202,6 @@ int run_forward(asm_head* h, const float* X, int B, const void* labels, int labe
     s.pdl = (h->pdl && !h->profiling && cs == cudaStreamCaptureStatusNone) ? 1 : 0;
   }
   h->fwd_valid = false;
-  CU_TRY(h, cudaMemsetAsync(s.flags, 0, 4, stream));
   if (h->l2_persist_bytes && h->cfg.mode == ASM_MODE_BF16 && (!h->l2_set || h->l2_stream != stream)) {
     // keep the bf16 operand copy of W (read by four kernels per step) resident in L2
     cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, h->l2_persist_bytes);
@@ -255,6 +256,7 @@ int run_backward(asm_head* h, const float* stats_all, int n_shards, float* loss_
   s.dW = dW;
   s.Wmut = const_cast<float*>(s.W);       // only written when an optimizer is armed
   const bool tc = h->tc;
+  s.defer_loss = (grads && tc && h->defer_loss) ? 1 : 0;   // the tcgen05 dX kernel reduces the loss
   if (stats_all) {
     // profiling: the gap between the two halves is the host-side statistics all-gather
     if (h->profiling && h->n_marks > 0 && h->n_marks < asm_head::kMaxMarks)
@@ -339,6 +341,7 @@ int asm_create(asm_head** out, const asm_config* cfg) {
   if ((e = getenv("ASM_UMMA_CG"))) h->tune.cg_mask = (uint32_t)atoi(e);
   if ((e = getenv("ASM_NO_OVERLAP")) && atoi(e)) h->overlap = false;
   if ((e = getenv("ASM_PDL"))) h->pdl = atoi(e) != 0;
+  if ((e = getenv("ASM_DEFER_LOSS"))) h->defer_loss = atoi(e) != 0;
   if (cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess) {
@@ -629,11 +632,15 @@ int asm_get_profile(asm_head* h, int32_t max_n, float* ms_out, char* names_out) 
 
 int asm_check_labels(asm_head* h, void* cuda_stream) {
   if (!h) return ASM_ERR_INVALID_ARG;
-  int flags = 0;
-  CU_TRY(h, cudaMemcpyAsync(&flags, h->st.flags, 4, cudaMemcpyDeviceToHost,
+  // the norm kernel marks out-of-range labels in its label -> local-class table
+  const int B = h->st.B;
+  if (B <= 0) return ASM_OK;
+  std::vector<int> yl((size_t)B);
+  CU_TRY(h, cudaMemcpyAsync(yl.data(), h->st.ylocal, (size_t)B * 4, cudaMemcpyDeviceToHost,
                             (cudaStream_t)cuda_stream));
   CU_TRY(h, cudaStreamSynchronize((cudaStream_t)cuda_stream));
-  if (flags & 1) return fail(h, ASM_ERR_LABEL_RANGE, "label outside [0, C_total)%s", "");
+  for (int i = 0; i < B; ++i)
+    if (yl[i] == -2) return fail(h, ASM_ERR_LABEL_RANGE, "label outside [0, C_total)%s", "");
   return ASM_OK;
 }
 

@@ -111,8 +111,8 @@ struct Step {
   float* dW;                 // [D, C]
   float* loss;               // scalar
   // workspace (device)
-  int* ylocal;               // [B]   y - class_offset if owned else -1
-  int* flags;                // [1]   bit0: label out of range
+  int* ylocal;               // [B]   y - class_offset if owned, -1 if another shard's, -2 if out of range
+  int* flags;                // [1]   (unused)
   float* n;                  // [B]
   float* inv_n;              // [B]
   float* inv_c;              // [Cp]  1/||w_j|| (0 on pad columns)
@@ -147,6 +147,7 @@ struct Step {
   // addressed as base + (*par_step & 1) * stride on the device (CUDA-graph friendly)
   const unsigned* par_step;
   int pdl;                   // launch dependents programmatically (eager, non-captured streams)
+  int defer_loss;            // the mean-loss reduction runs in an idle warp of the dX kernel, not in combine
   size_t stats_par_stride, dx_par_stride;   // in floats
 };
 

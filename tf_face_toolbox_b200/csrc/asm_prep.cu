@@ -112,9 +112,10 @@ __global__ void __launch_bounds__(256) prep_kernel(Step s, const void* labels, i
       s.inv_n[row] = nn > 0.f ? 1.0f / nn : 0.f;
       long long y = label_bytes == 8 ? reinterpret_cast<const long long*>(labels)[row]
                                      : (long long)reinterpret_cast<const int*>(labels)[row];
-      if (y < 0 || y >= s.C_total) atomicOr(s.flags, 1);
+      // -1: owned by another shard; -2: outside [0, C_total) (reported by asm_check_labels;
+      // both mean "no target column here" to every kernel, so a bad label never faults)
       const long long yl = y - s.class_offset;
-      s.ylocal[row] = (yl >= 0 && yl < s.C) ? (int)yl : -1;
+      s.ylocal[row] = (y < 0 || y >= s.C_total) ? -2 : ((yl >= 0 && yl < s.C) ? (int)yl : -1);
       s.tgt_s[row] = 0.f;
       s.tgt_f[row] = 0.f;
     }
@@ -209,6 +210,10 @@ __global__ void __launch_bounds__(256) combine_kernel(Step s, const float* stats
   const int lane = threadIdx.x & 31;
   if (row < s.B) {
     float m = -INFINITY, z = 0.f, fy = 0.f;
+    // per-row scalars of the epilogue below: issued up front (warp-uniform addresses) so that
+    // they travel together with the partials instead of adding a second memory round trip
+    const int yl_row = s.ylocal[row];
+    const float tgt_f_row = s.tgt_f[row], tgt_s_row = s.tgt_s[row], inv_n_row = s.inv_n[row];
     if (FUSED) {
       const float2* p = s.part + (size_t)row * s.NT;
       for (int t = lane; t < s.NT; t += 32) {
@@ -230,9 +235,9 @@ __global__ void __launch_bounds__(256) combine_kernel(Step s, const float* stats
       fy += __shfl_xor_sync(0xffffffffu, fy, o);
     }
     if (lane == 0) {
-      const bool owned = s.ylocal[row] >= 0;
+      const bool owned = yl_row >= 0;
       if (FUSED) {
-        fy = owned ? s.tgt_f[row] : 0.f;
+        fy = owned ? tgt_f_row : 0.f;
         s.stats_local[row] = m;
         s.stats_local[s.B + row] = z;
         s.stats_local[2 * s.B + row] = fy;
@@ -243,11 +248,11 @@ __global__ void __launch_bounds__(256) combine_kernel(Step s, const float* stats
       s.rowloss[row] = lse - fy;
       float gt = 0.f, r = 0.f;
       if (owned) {
-        const float inv_n = s.inv_n[row];
+        const float inv_n = inv_n_row;
         float psi, dpsi;
-        const float t = fminf(1.f, fmaxf(-1.f, s.tgt_s[row] * inv_n));
+        const float t = fminf(1.f, fmaxf(-1.f, tgt_s_row * inv_n));
         psi_eval(t, s.m, psi, dpsi);
-        const float gy = (expf(s.tgt_f[row] - lse) - 1.0f) * s.invB;
+        const float gy = (expf(tgt_f_row - lse) - 1.0f) * s.invB;
         const float lam = step_lambda(s.lambda, s.lambda_dev);
         const float il = 1.0f / (1.0f + lam);
         gt = gy * (lam + dpsi) * il;
@@ -257,6 +262,9 @@ __global__ void __launch_bounds__(256) combine_kernel(Step s, const float* stats
       s.rcoef[row] = r;
     }
   }
+  // With gradients the backward kernels do not need the mean loss: its reduction is deferred
+  // to an idle warp of the dX kernel so that the recompute kernel can start right away.
+  if (s.defer_loss) return;
   // last block done: fixed-order sum of the per-row losses
   __threadfence();
   __syncthreads();

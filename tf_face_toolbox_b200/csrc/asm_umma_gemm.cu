@@ -342,6 +342,26 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
         }
       }
     }
+    if (KIND == U_DX && s.defer_loss && blockIdx.x == 0) {
+      // Deferred mean loss.  One warp reproduces, bit for bit, the fixed-order reduction of
+      // combine_kernel's last block: 256 strided partial sums, then the pairwise tree
+      // (offsets 128, 64, 32 stay inside a lane, 16..1 go through shuffles).
+      float part[8];
+#pragma unroll
+      for (int v = 0; v < 8; ++v) {
+        float acc = 0.f;
+        for (int i = v * 32 + lane; i < s.B; i += 256) acc += __ldcg(s.rowloss + i);
+        part[v] = acc;
+      }
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1)
+#pragma unroll
+        for (int v = 0; v < o; ++v) part[v] += part[v + o];
+      float r = part[0];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) r += __shfl_down_sync(0xffffffffu, r, o);
+      if (lane == 0 && s.loss) *s.loss = r * s.invB;
+    }
   } else if (warp >= 4) {
     // ------------------------------------------------------------ epilogue (256 threads)
     const int q4 = warp & 3;                  // TMEM lane quarter this warp may access
