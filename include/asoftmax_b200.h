@@ -58,7 +58,10 @@ typedef struct {
   int32_t class_offset;  /* shard owns [class_offset, class_offset + C_local)       */
   int32_t B_max;         /* largest (global) batch this handle will see             */
   int32_t m;             /* margin, 1..4                                            */
-  int32_t mode;          /* ASM_MODE_FP32 | ASM_MODE_BF16 (bf16 operands, fp32 acc) */
+  int32_t mode;          /* ASM_MODE_BF16: X, W rounded to bf16 (RNE), fp32 accumulate (D % 64 == 0).
+                            ASM_MODE_FP32: all 24 significand bits of X and W are used -- on the
+                            tensor cores through an exact three-plane bf16 split when D % 64 == 0,
+                            on CUDA cores otherwise (D % 16 == 0). */
   int32_t rank, world;   /* informational; world == 1 -> single shard               */
   void*   nccl_comm;     /* reserved, must be NULL: collectives are issued by the
                             host between asm_forward_partial / asm_backward_partial */
