@@ -46,6 +46,22 @@ def main():
         good = rel <= tol and cx >= 0.9999 and cw >= 0.9999
         ok &= good
         print(f"rank {rank}/{world} {mode} B={B} C={C}: loss_rel={rel:.2e} cos_dX={cx:.6f} cos_dW={cw:.6f} {'OK' if good else 'FAIL'}", flush=True)
+        # one more step with the optimizer fused into the shard's dW kernel (data_parallel.py:
+        # 186-196 without the G-fold redundancy): first momentum step => W -= lr (dW + wd W)
+        from tf_face_toolbox_b200 import FusedOptimizer
+        lr, wd = 0.05, 5e-4
+        W_before = head.weights.clone()
+        opt = FusedOptimizer("Momentum", lr=lr, weight_decay=wd)
+        loss2, dX2, none_dW = head.step(inp.X[rank * b:(rank + 1) * b].to(dev), inp.y[rank * b:(rank + 1) * b].to(dev),
+                                        5.0, optimizer=opt)
+        torch.cuda.synchronize()
+        expect = W_before - lr * (dW + wd * W_before)
+        upd = (head.weights - W_before).double().flatten()
+        exp_upd = (expect - W_before).double().flatten()
+        cu = float(upd @ exp_upd / torch.sqrt((upd @ upd) * (exp_upd @ exp_upd)))
+        good2 = none_dW is None and cu >= 0.9999 and abs(float(loss2) - float(loss)) <= 1e-6 * abs(float(loss))
+        ok &= good2
+        print(f"rank {rank}/{world} {mode} fused optimizer: cos(update)={cu:.6f} {'OK' if good2 else 'FAIL'}", flush=True)
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)

@@ -402,3 +402,27 @@ def test_host_pipelined_step_returns_every_loss_in_order():
             got.append(prev)
     got.append(runner.flush())
     assert got == want
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_sharded_head_fused_optimizer_matches_single_call(mode):
+    """The class-sharded head's step(optimizer=...) (asm_forward_partial / asm_backward_partial
+    with the update fused into the shard's dW kernel) equals the single-shard fused call."""
+    from tf_face_toolbox_b200 import FusedOptimizer, ShardedASoftmaxHead
+    dev = torch.device("cuda:0")
+    inp = make_inputs(256, 128, 3000, seed=9)
+    X, y = inp.X.to(dev), inp.y.to(dev)
+    head = ShardedASoftmaxHead(128, 3000, m=4, mode=mode, device=dev, weights_full=inp.W)   # world 1
+    W = inp.W.to(dev).clone()
+    o1, o2 = FusedOptimizer("Momentum", lr=0.05), FusedOptimizer("Momentum", lr=0.05)
+    for _ in range(3):
+        l1, dX1, none_dW = head.step(X, y, 5.0, optimizer=o1)
+        l2, _, dX2, _ = asoftmax_head(X, y, 3000, 4, 5.0, weights=W, mode=mode, optimizer=o2)
+        assert none_dW is None
+    torch.cuda.synchronize()
+    assert float(l1) == pytest.approx(float(l2), rel=1e-6)
+    torch.testing.assert_close(head.weights, W, rtol=1e-5, atol=1e-8)
+    torch.testing.assert_close(o1.state0, o2.state0, rtol=1e-5, atol=1e-10)
+    torch.testing.assert_close(dX1, dX2, rtol=1e-5, atol=1e-9)
+    assert not torch.equal(W, inp.W.to(dev))                      # the weights did move

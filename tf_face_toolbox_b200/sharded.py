@@ -60,16 +60,24 @@ class _CudaShard:
         self._keep = (X, y, W)          # borrowed until backward_partial has been enqueued
         return stats
 
-    def backward_partial(self, stats_all, X, W):
+    def backward_partial(self, stats_all, X, W, optimizer=None):
         B = X.shape[0]
         h = self._handle(B)
         loss = torch.empty(1, device=X.device, dtype=torch.float32)
         dXp = torch.empty_like(X)
-        dW = torch.empty_like(W)
+        dW = torch.empty_like(W) if optimizer is None else None     # fused update: dW never exists
         stream = C.c_void_p(torch.cuda.current_stream(X.device).cuda_stream)
         with torch.cuda.device(X.device):
-            _lib.check(h.lib.asm_backward_partial(h.ptr, stats_all.data_ptr(), stats_all.shape[0],
-                                                  loss.data_ptr(), dXp.data_ptr(), dW.data_ptr(), stream), h.ptr)
+            if optimizer is not None:
+                optimizer._arm(h, W)
+            try:
+                rc = h.lib.asm_backward_partial(h.ptr, stats_all.data_ptr(), stats_all.shape[0],
+                                                loss.data_ptr(), dXp.data_ptr(),
+                                                dW.data_ptr() if dW is not None else None, stream)
+            finally:
+                if optimizer is not None:
+                    optimizer._disarm(h)
+            _lib.check(rc, h.ptr)
         return loss[0], dXp, dW
 
 
@@ -146,7 +154,7 @@ class ShardedASoftmaxHead:
         _lib.check(h.lib.asm_p2p_attach(h.ptr, ptrs), h.ptr)
         return dict(handle=h, buf=buf, hdl=hdl, batch=batch_global)
 
-    def _step_p2p(self, embeddings_local, labels_local, lam, p2p=None):
+    def _step_p2p(self, embeddings_local, labels_local, lam, p2p=None, optimizer=None):
         p2p = p2p or self._p2p
         h = p2p["handle"]
         X = embeddings_local.contiguous()
@@ -154,28 +162,43 @@ class ShardedASoftmaxHead:
         b = X.shape[0]
         loss = torch.empty(1, device=X.device, dtype=torch.float32)
         dX = torch.empty_like(X)
-        dW = torch.empty_like(self.weights)
+        dW = torch.empty_like(self.weights) if optimizer is None else None
         stream = C.c_void_p(torch.cuda.current_stream(X.device).cuda_stream)
         with torch.cuda.device(X.device):
-            _lib.check(h.lib.asm_step_p2p(h.ptr, X.data_ptr(), b, y.data_ptr(), y.element_size(),
-                                          self.weights.data_ptr(), lam, loss.data_ptr(), dX.data_ptr(),
-                                          dW.data_ptr(), stream), h.ptr)
+            if optimizer is not None:
+                optimizer._arm(h, self.weights)
+            try:
+                rc = h.lib.asm_step_p2p(h.ptr, X.data_ptr(), b, y.data_ptr(), y.element_size(),
+                                        self.weights.data_ptr(), lam, loss.data_ptr(), dX.data_ptr(),
+                                        dW.data_ptr() if dW is not None else None, stream)
+            finally:
+                if optimizer is not None:
+                    optimizer._disarm(h)
+            _lib.check(rc, h.ptr)
         return loss[0], dX, dW
 
     # ---- one training step of the head -------------------------------------------------
-    def step(self, embeddings_local: torch.Tensor, labels_local: torch.Tensor, lambda_state=None):
+    def step(self, embeddings_local: torch.Tensor, labels_local: torch.Tensor, lambda_state=None,
+             optimizer=None):
         """embeddings_local [B/G, D], labels_local [B/G] (this rank's data-parallel slice,
         data_parallel.py:206-207).  Returns (loss, dX_local [B/G, D], dW_local [D, C_local]);
-        loss is the global-batch mean and identical on every rank."""
+        loss is the global-batch mean and identical on every rank.
+        With `optimizer` (a FusedOptimizer owned by this rank) the shard's weights and optimizer
+        state are updated in place inside the dW kernel and dW_local is None: this is the
+        per-tower `apply_gradients` of data_parallel.py:186-196 without the G-fold redundancy --
+        each class column is updated exactly once, on the rank that owns it."""
         lam = _as_lambda(lambda_state) if lambda_state is not None else self.lambda_state.step()
         if self._p2p is not None:
-            return self._step_p2p(embeddings_local, labels_local, lam)
+            return self._step_p2p(embeddings_local, labels_local, lam, optimizer=optimizer)
         b = embeddings_local.shape[0]
         X = self._all_gather(embeddings_local).reshape(-1, self.D)
         y = self._all_gather(labels_local).reshape(-1)
         stats = self.compute.forward_partial(X, y, self.weights, lam)             # [3, B]
         stats_all = self._all_gather(stats).reshape(self.world, 3, X.shape[0])    # [G, 3, B]
-        loss, dX_partial, dW = self.compute.backward_partial(stats_all, X, self.weights)
+        if optimizer is not None:
+            loss, dX_partial, dW = self.compute.backward_partial(stats_all, X, self.weights, optimizer=optimizer)
+        else:
+            loss, dX_partial, dW = self.compute.backward_partial(stats_all, X, self.weights)
         dX_local = self._reduce_scatter_rows(dX_partial, b)
         return loss, dX_local, dW
 
