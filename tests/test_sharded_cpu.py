@@ -124,3 +124,90 @@ def test_shard_bounds_cover_all_classes():
         for (a0, a1), (b0, b1) in zip(spans, spans[1:]):
             assert a1 == b0
     assert shard_bounds(85742, 8, 7) == (75026, 85742)
+
+
+# ---------------------------------------------------------------------------------------
+# Train-loop glue: data-parallel backbone (DDP) + class-parallel head.
+# examples/train_sphereface20.py::head_step must reproduce single-process training on the
+# full batch -- in particular the `* world` that turns DDP's gradient mean into the sum the
+# global-batch mean loss needs (the mirror of data_parallel.py:37 + :179).
+# ---------------------------------------------------------------------------------------
+def _load_example():
+    import importlib.util
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples",
+                        "train_sphereface20.py")
+    spec = importlib.util.spec_from_file_location("train_sphereface20", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def _tiny_net():
+    torch.manual_seed(3)
+    return torch.nn.Sequential(torch.nn.Flatten(), torch.nn.Linear(24, 32), torch.nn.Tanh(), torch.nn.Linear(32, 16))
+
+
+def _glue_data(B, C):
+    g = torch.Generator().manual_seed(11)
+    return torch.randn(B, 2, 3, 4, generator=g), torch.randint(0, C, (B,), generator=g, dtype=torch.int32)
+
+
+def _glue_worker(rank, world, port, B, C, steps, lr, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        ex = _load_example()
+        net = torch.nn.parallel.DistributedDataParallel(_tiny_net())
+        opt = torch.optim.SGD(net.parameters(), lr=lr)
+        W0 = make_inputs(B, 16, C, seed=5, w_std=0.05).W
+        lo, hi = shard_bounds(C, world, rank)
+        head = ShardedASoftmaxHead(16, C, m=4, mode="fp32", device="cpu", weights_full=W0,
+                                   shard_compute=OracleShard(lo, hi, 4))
+
+        def head_call(feats, labels):
+            loss, dX, dW = head.step(feats, labels, 5.0)
+            head.weights.sub_(lr * dW)                       # plain SGD on the shard
+            return loss, dX
+        images, labels = _glue_data(B, C)
+        b = B // world
+        for _ in range(steps):
+            ex.head_step(net, images[rank * b:(rank + 1) * b], labels[rank * b:(rank + 1) * b], head_call, opt,
+                         world=world, clip=0, autocast=False)
+        Wfull = head.gather_weights()
+        q.put((rank, [p.detach().numpy().copy() for p in net.module.parameters()], Wfull.numpy()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_ddp_backbone_plus_sharded_head_equals_single_process_training():
+    B, C, steps, lr, world = 12, 37, 3, 0.5, 2
+    # single process, full batch, oracle head
+    ex = _load_example()
+    net = _tiny_net()
+    opt = torch.optim.SGD(net.parameters(), lr=lr)
+    W = make_inputs(B, 16, C, seed=5, w_std=0.05).W.clone()
+    images, labels = _glue_data(B, C)
+
+    def head_call(feats, y):
+        r = ref.asoftmax_head(feats.numpy(), W.numpy(), y.numpy(), 4, 5.0)
+        W.sub_(lr * torch.from_numpy(r.dW).float())
+        return torch.tensor(r.loss), torch.from_numpy(r.dX).float()
+    for _ in range(steps):
+        ex.head_step(net, images, labels, head_call, opt, world=1, clip=0, autocast=False)
+    want = [p.detach().numpy() for p in net.parameters()]
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_glue_worker, args=(r, world, port, B, C, steps, lr, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    outs = [q.get(timeout=180) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, params, Wfull in outs:
+        for got, exp in zip(params, want):
+            np.testing.assert_allclose(got, exp, rtol=2e-4, atol=1e-6)
+        np.testing.assert_allclose(Wfull, W.numpy(), rtol=2e-4, atol=1e-7)
