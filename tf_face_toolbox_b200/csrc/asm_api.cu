@@ -28,7 +28,7 @@ struct asm_head {
   int maps_B = -1;
   bool defer_loss = true;        // ASM_DEFER_LOSS=0: combine reduces the loss itself (A/B knob)
   bool tc = false;               // tcgen05 kernels (bf16 mode, or fp32 mode through bf16 planes)
-  UmmaTuning tune{8192, 1024, 2048, 15, 0};   // CTA pairs on all four kernels (ASM_UMMA_CG=0: single-CTA)
+  UmmaTuning tune{8192, 1024, 2048, 15, 0, 0};   // CTA pairs on all four kernels (ASM_UMMA_CG=0: single-CTA)
   bool fwd_valid = false;
   // dX branch of the backward (DX + dx_finish) runs on a second stream so that it fills the
   // SMs the DW kernel's tail leaves idle; both only depend on G'' from the BWDG kernel
@@ -97,7 +97,7 @@ Layout make_layout(const asm_config& c, int num_sms) {
   L.Cp = (int)align_up(c.C_local, 256);
   L.NT = (L.Cp + 127) / 128;
   if (L.NT < 2 * num_sms) L.NT = 2 * num_sms;   // tcgen05 forward: 2 partials per CTA
-  L.MT = 2 * (int)((B + 255) / 256);      // >= ceil(B/128): covers both paths
+  L.MT = 2 * (int)((B + 127) / 128);      // two per batch tile, down to 128-row tiles
   // dX split-K partial capacity: the larger of both paths at B_max, but never less than
   // what a single 128-row tile would use (KS grows when B shrinks).
   const int ks_simt = simt_dx_splits(c.B_max, c.D, L.Cp);
@@ -192,7 +192,8 @@ int run_forward(asm_head* h, const float* X, int B, const void* labels, int labe
   s.X = X;
   s.W = W;
   s.logits = logits;
-  s.MT = h->tc ? umma_q_parts(B) : (B + kRowTileHost - 1) / kRowTileHost;
+  s.MT = h->tc ? umma_q_parts(B, umma_tile_width(h->tune, (h->tune.cg_mask & 2) ? 2 : 1))
+               : (B + kRowTileHost - 1) / kRowTileHost;
   h->launches = 0;
   h->n_marks = 0;
   {
@@ -221,7 +222,11 @@ int run_forward(asm_head* h, const float* X, int B, const void* labels, int labe
   if (h->tc) {
     if ((B + 127) / 128 > h->num_sms)
       return fail(h, ASM_ERR_INVALID_ARG, "batch too large for the tcgen05 forward grid%s", "");
-    s.NT = umma_forward_tiles(B, s.Cp, h->num_sms, (h->tune.cg_mask & 1) ? 2 : 1);
+    {
+      const int fcg = (h->tune.cg_mask & 1) ? 2 : 1;
+      // narrow tiles only with CTA pairs, and the forward pairs need at least two row tiles
+      s.NT = umma_forward_tiles(B, s.Cp, h->num_sms, fcg, umma_tile_width(h->tune, (fcg == 2 && B > 128) ? 2 : 1));
+    }
     s.KS = umma_dx_splits(B, s.D, s.Cp, h->num_sms, (h->tune.cg_mask & 8) ? 2 : 1);
     if (h->maps_B != B) {
       if (!umma_build_maps(&h->maps, s))
@@ -339,6 +344,7 @@ int asm_create(asm_head** out, const asm_config* cfg) {
   if ((e = getenv("ASM_UMMA_MN_KSTEP"))) h->tune.mn_kstep = (uint32_t)atoi(e);
   if ((e = getenv("ASM_UMMA_DEBUG"))) h->tune.debug_flags = (uint32_t)atoi(e);
   if ((e = getenv("ASM_UMMA_CG"))) h->tune.cg_mask = (uint32_t)atoi(e);
+  if ((e = getenv("ASM_UMMA_BN"))) h->tune.bn = (uint32_t)atoi(e);   // 128: narrow tiles (not validated on hardware yet)
   if ((e = getenv("ASM_NO_OVERLAP")) && atoi(e)) h->overlap = false;
   if ((e = getenv("ASM_PDL"))) h->pdl = atoi(e) != 0;
   if ((e = getenv("ASM_DEFER_LOSS"))) h->defer_loss = atoi(e) != 0;

@@ -178,6 +178,7 @@ struct UmmaTuning {          // MN-major shared-memory descriptor parameters (by
   uint32_t mn_lbo, mn_sbo, mn_kstep;
   uint32_t cg_mask;          // CTA pairs (cta_group::2) per kernel: bit0 FWD, bit1 BWDG, bit2 DW, bit3 DX
   uint32_t debug_flags;      // bit0: skip epilogue math, bit1: DW without stores, bit2: X-resident forward variant (ASM_UMMA_DEBUG, bring-up only)
+  uint32_t bn;               // tile width along N of FWD / BWDG / DW: 0 or 256 = default, 128 = narrow (ASM_UMMA_BN)
 };
 struct UmmaArgs {
   int mt, nt, ks, kb_total, kb_per;
@@ -191,9 +192,10 @@ struct UmmaArgs {
 };
 cudaError_t umma_configure();
 bool umma_build_maps(UmmaMaps* m, const Step& s);
-int umma_forward_tiles(int B, int Cp, int num_sms, int cg);
-int umma_forward_grid(int B, int Cp, int num_sms, int cg);
-int umma_q_parts(int B);
+int umma_tile_width(const UmmaTuning& tu, int cg);
+int umma_forward_tiles(int B, int Cp, int num_sms, int cg, int bn = 256);
+int umma_forward_grid(int B, int Cp, int num_sms, int cg, int bn = 256);
+int umma_q_parts(int B, int bn = 256);
 int umma_dx_splits(int B, int D, int Cp, int num_sms, int cg);
 void launch_umma_forward(const Step& s, const UmmaMaps& m, const UmmaTuning& tu, int num_sms,
                          cudaStream_t st);

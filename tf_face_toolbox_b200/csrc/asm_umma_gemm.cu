@@ -28,6 +28,7 @@ namespace asmh {
 
 namespace {
 constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4;
+constexpr int BN_FULL = BN;                   // widest tile: sizes the per-tile vectors and the TMEM stage stride
 constexpr int A_BYTES = BM * BK * 2;           // 16 KB
 constexpr int B_BYTES = BN * BK * 2;           // 32 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES; // 48 KB
@@ -58,7 +59,8 @@ enum { U_FWD = 0, U_BWDG = 1, U_DW = 2, U_DX = 3, U_FWDR = 4, U_DWOPT = 5, U_DWF
 // pipeline geometry per kernel kind
 // CG = 2: a CTA pair (cluster of 2, cta_group::2) computes one 256 x 256 tile; each CTA
 // stages its own 128 A rows and HALF of the B tile, so a stage is 32 KB and the ring is 6 deep.
-template <int KIND, int CG = 1> struct Geo {
+// BNT: tile width along N (256, or 128 for shards whose unit count does not fill the pairs)
+template <int KIND, int CG = 1, int BNT = BN_FULL> struct Geo {
   static constexpr bool RES = (KIND == U_FWDR);
   static constexpr int KB = (RES && CG == 1) ? 32 : BK;    // K elements per pipeline stage
   // the dW kernel of a CTA pair trades its 6th operand stage for a 4-deep weight-chunk ring
@@ -67,7 +69,7 @@ template <int KIND, int CG = 1> struct Geo {
   static constexpr int NSB = (KIND == U_BWDG && CG == 2) ? 2 : 1;   // G'' staging buffers per column half
   static constexpr int NST = RES ? 5 : (CG == 2 ? ((KIND == U_DW || KIND == U_BWDG) ? 5 : 6) : STAGES);   // pipeline depth
   static constexpr int A_ST = RES ? 0 : BM * KB * 2;       // A bytes per stage
-  static constexpr int B_ST = BN * KB * 2 / CG;            // B bytes per stage (per CTA)
+  static constexpr int B_ST = BNT * KB * 2 / CG;           // B bytes per stage (per CTA)
   static constexpr int ST_B = A_ST + B_ST;
   static constexpr int RES_B = RES ? 8 * A_BYTES : 0;      // resident A block (K <= 512)
   static constexpr int CH_B = 64 * KB * 2;                 // one 64-wide MN-major chunk
@@ -109,11 +111,15 @@ __device__ __noinline__ float fwd_target(float* tgt_s, float* tgt_f, const float
 }
 }  // namespace
 
-template <int KIND, int CG = 1>
+template <int KIND, int CG = 1, int BNT = BN_FULL>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
             const __grid_constant__ CUtensorMap mapC, Step s, UmmaArgs g) {
-  using G_ = Geo<KIND, CG>;
+  using G_ = Geo<KIND, CG, BNT>;
+  constexpr int BN = BNT;                 // tile width of this instantiation (shadows the default)
+  constexpr int HC = BN / 2;              // accumulator columns per epilogue half
+  static_assert(BNT == 256 || BNT == 128, "tile width");
+  static_assert(BNT == 256 || (KIND != U_FWDR && KIND != U_BWDG1), "narrow tiles: main kinds only");
   pdl_trigger();      // the next kernel's CTAs may take over SMs as this grid's tail drains
   // CTA pair: rank within the cluster, work is distributed over PAIRS
   const int crank = CG == 2 ? (int)ptx::cluster_ctarank() : 0;
@@ -141,9 +147,9 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
   uint64_t* wempty = wfull + 8;                                       // DW: [half][buf]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(wempty + 8);
   constexpr int NWB = G_::NWB;
-  float* vec0 = reinterpret_cast<float*>(smem + PIPE_B + AUX_BARS);   // [2][BN]
-  float* vec1 = vec0 + 2 * BN;
-  float* vec2 = vec1 + 2 * BN;
+  float* vec0 = reinterpret_cast<float*>(smem + PIPE_B + AUX_BARS);   // [2][BN_FULL]
+  float* vec1 = vec0 + 2 * BN_FULL;
+  float* vec2 = vec1 + 2 * BN_FULL;
   uint8_t* stg = smem + PIPE_B + AUX_BARS + AUX_VEC;                  // BWDG: [2 halves][NSB][STG_HALF]
   constexpr int NSB = G_::NSB;
   uint8_t* wbuf = smem + PIPE_B + AUX_BARS;                           // DW: [2][2][WB_BUF]
@@ -249,7 +255,7 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
             if (B_MN) {
 #pragma unroll
               for (int c = 0; c < BN / 128; ++c)
-                ptx::tma_load_2d_cg2(sB + c * CH_B, &mapB, &full[st], nB + (crank * 2 + c) * 64, kB);
+                ptx::tma_load_2d_cg2(sB + c * CH_B, &mapB, &full[st], nB + (crank * (BN / 128) + c) * 64, kB);
             } else {
               ptx::tma_load_2d_cg2(sB, &mapB, &full[st], kB, nB + crank * (BN / 2));
             }
@@ -291,7 +297,7 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
         const uint32_t a = lt & 1, aph = (lt >> 1) & 1;
         ptx::mbar_wait(&tempty[a], aph ^ 1);
         ptx::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + a * BN;
+        const uint32_t d_tmem = tmem_base + a * BN_FULL;
         for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int st = it % NST;
           const uint32_t ph = (it / NST) & 1;
@@ -330,14 +336,14 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
         int z, m_idx, n_idx;
         decode(u, z, m_idx, n_idx);
         m_idx = m_idx * CG + crank;
-        for (int c = 0; c < 4; ++c, ++cc) {
+        for (int c = 0; c < BN / 64; ++c, ++cc) {
           const uint32_t buf = cc % NWB, ph = (cc / NWB) & 1;
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             ptx::mbar_wait(&wempty[h * NWB + buf], ph ^ 1);
             ptx::mbar_expect_tx(&wfull[h * NWB + buf], WB_BUF);
             ptx::tma_load_2d(wbuf + (h * NWB + buf) * WB_BUF, &mapC, &wfull[h * NWB + buf],
-                             m_idx * BM, n_idx * BN + h * 128 + c * 32);
+                             m_idx * BM, n_idx * BN + h * HC + c * 32);
           }
         }
       }
@@ -368,7 +374,7 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
     const int half = (warp - 4) >> 2;         // which 128 of the 256 accumulator columns
     const int et = threadIdx.x - 128;         // 0..255
     const int lane_row = q4 * 32 + lane;      // row of the tile owned by this thread
-    const int col0 = half * 128;
+    const int col0 = half * HC;
     uint32_t lt = 0;
     // per-tile vectors are fetched one tile ahead into registers (pre0..2) and published to
     // shared memory at the start of their tile, so no global-load latency is exposed
@@ -382,7 +388,7 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
       int pz, pm, pn;
       decode(pu, pz, pm, pn);
       pm = pm * CG + crank;
-      if (IS_FWD) pre0 = s.inv_c[pn * BN + et];
+      if (IS_FWD) pre0 = s.inv_c[pn * BN + (BN == BN_FULL ? et : (et & (BN - 1)))];
       if (IS_BWDG) {
         const int i = pn * BN + et;
         const bool iv = i < s.B;
@@ -420,10 +426,10 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
       const int m0 = m_idx * BM, n0 = n_idx * BN;
       const uint32_t a = lt & 1, aph = (lt >> 1) & 1;
       const uint32_t taddr =
-          tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + a * BN + col0;
-      float* v0 = vec0 + a * BN;
-      float* v1 = vec1 + a * BN;
-      float* v2 = vec2 + a * BN;
+          tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + a * BN_FULL + col0;
+      float* v0 = vec0 + a * BN_FULL;
+      float* v1 = vec1 + a * BN_FULL;
+      float* v2 = vec2 + a * BN_FULL;
       uint32_t r0[32], r1[32];
       if (g.debug_flags & 1) {                // bring-up knob: mainloop only, no epilogue math
         ptx::mbar_wait(&tfull[a], aph);
@@ -439,12 +445,12 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
 #define ASM_EPILOGUE_CHUNKS(process)                       \
       ptx::tmem_ld32(taddr, r0);                           \
       _Pragma("unroll 1")                                  \
-      for (int cp = 0; cp < 2; ++cp) {                     \
+      for (int cp = 0; cp < BN / 128; ++cp) {              \
         ptx::tmem_ld_wait_dep(r0);                         \
         ptx::tmem_ld32(taddr + cp * 64 + 32, r1);          \
         process(r0, cp * 2);                               \
         ptx::tmem_ld_wait_dep(r1);                         \
-        if (cp == 0) {                                     \
+        if (cp + 1 < BN / 128) {                           \
           ptx::tmem_ld32(taddr + 64, r0);                  \
         } else {                                           \
           release_acc(a);                                  \
@@ -598,7 +604,7 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
         ptx::mbar_wait(&tfull[a], aph);
         ptx::tc_fence_after();
         auto process = [&](const uint32_t (&r)[32], int c) {
-          const uint32_t cc = lt * 4 + c;                     // chunk counter of this half
+          const uint32_t cc = lt * (BN / 64) + c;             // chunk counter of this half
           const uint32_t buf = cc % NWB, ph = (cc / NWB) & 1;
           const unsigned short* wsm =
               reinterpret_cast<const unsigned short*>(wbuf + (half * NWB + buf) * WB_BUF) + lane_row;
@@ -689,7 +695,7 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
         ptx::tc_fence_after();
         auto process = [&](const uint32_t (&r)[32], int c) {
           const int db = d_first + c * 32;
-          if (c < 3) prefetch_chunk(m0, db + 32);
+          if (c < BN / 64 - 1) prefetch_chunk(m0, db + 32);
           else if (nm0 >= 0) prefetch_chunk(nm0, nd_first);
           if (!jv || db >= s.D) return;
 #pragma unroll
@@ -787,23 +793,28 @@ bool encode_map(CUtensorMap* m, const void* base, uint64_t inner, uint64_t outer
 // are used per kernel kind when the M extent has at least two 128-row tiles.
 static int fwd_cg(int B, int cg) { return (cg == 2 && B > BM) ? 2 : 1; }
 
+// Tile width along N of FWD (classes), BWDG (batch rows) and DW (d): 256, or 128 when the
+// tuning asks for it and the kernel runs as CTA pairs.  (Narrow tiles double the number of
+// work units; see DESIGN.md section 9, wave quantisation on small shards.)
+int umma_tile_width(const UmmaTuning& tu, int cg) { return (tu.bn == 128 && cg == 2) ? 128 : BN_FULL; }
+
 // FWD grid: a multiple of the number of row tiles so each CTA keeps one set of rows
-int umma_forward_grid(int B, int Cp, int num_sms, int cg) {
+int umma_forward_grid(int B, int Cp, int num_sms, int cg, int bn) {
   cg = fwd_cg(B, cg);
   const int mt = ((B + BM - 1) / BM + cg - 1) / cg;      // row tiles of 128*cg rows
-  const int total = mt * (Cp / BN);
+  const int total = mt * (Cp / bn);
   const int units = num_sms / cg;                          // CTAs or CTA pairs
   if (mt > units) return 0;
   const int g = (units / mt) * mt;
   return (g < total ? g : total) * cg;
 }
 // (max, sum-exp) partials per row written by FWD: one per column half per CTA of that row tile
-int umma_forward_tiles(int B, int Cp, int num_sms, int cg) {
+int umma_forward_tiles(int B, int Cp, int num_sms, int cg, int bn) {
   const int c = fwd_cg(B, cg);
   const int mt = ((B + BM - 1) / BM + c - 1) / c;
-  return 2 * (umma_forward_grid(B, Cp, num_sms, cg) / c / mt);
+  return 2 * (umma_forward_grid(B, Cp, num_sms, cg, bn) / c / mt);
 }
-int umma_q_parts(int B) { return 2 * ((B + BN - 1) / BN); }            // 128-row partials
+int umma_q_parts(int B, int bn) { return 2 * ((B + bn - 1) / bn); }    // one partial per column half of a batch tile
 
 int umma_dx_splits(int B, int D, int Cp, int num_sms, int cg) {
   const int c = fwd_cg(B, cg);
@@ -883,20 +894,20 @@ static UmmaArgs base_args(const UmmaTuning& tu) {
 }
 
 namespace {
-template <int KIND, int CG>
+template <int KIND, int CG, int BNT = BN_FULL>
 cudaError_t set_smem() {
-  return cudaFuncSetAttribute(umma_kernel<KIND, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              Geo<KIND, CG>::SMEM);
+  return cudaFuncSetAttribute(umma_kernel<KIND, CG, BNT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              Geo<KIND, CG, BNT>::SMEM);
 }
 // launch with `units` work units (CTAs, or CTA pairs as clusters of 2)
-template <int KIND, int CG>
+template <int KIND, int CG, int BNT = BN_FULL>
 void launch_k(int units, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c,
               const Step& s, const UmmaArgs& g, cudaStream_t st) {
   if (units <= 0) return;
   // DW follows an event record (the dX fork), everything else follows a kernel directly
   const bool pdl = s.pdl != 0 && KIND != U_DW && KIND != U_DWOPT && KIND != U_DWF;
-  launch_pdl(umma_kernel<KIND, CG>, dim3(units * CG), dim3(NUM_THREADS), Geo<KIND, CG>::SMEM, st, pdl,
-             CG, a, b, c, s, g);
+  launch_pdl(umma_kernel<KIND, CG, BNT>, dim3(units * CG), dim3(NUM_THREADS), Geo<KIND, CG, BNT>::SMEM, st,
+             pdl, CG, a, b, c, s, g);
 }
 }  // namespace
 
@@ -916,7 +927,13 @@ cudaError_t umma_configure() {
   if ((e = set_smem<U_DWF, 1>()) != cudaSuccess) return e;
   if ((e = set_smem<U_DWF, 2>()) != cudaSuccess) return e;
   if ((e = set_smem<U_DX, 1>()) != cudaSuccess) return e;
-  return set_smem<U_DX, 2>();
+  if ((e = set_smem<U_DX, 2>()) != cudaSuccess) return e;
+  // 128-wide tiles (UmmaTuning::bn, ASM_UMMA_BN=128): CTA-pair kernels only
+  if ((e = set_smem<U_FWD, 2, 128>()) != cudaSuccess) return e;
+  if ((e = set_smem<U_BWDG, 2, 128>()) != cudaSuccess) return e;
+  if ((e = set_smem<U_DW, 2, 128>()) != cudaSuccess) return e;
+  if ((e = set_smem<U_DWOPT, 2, 128>()) != cudaSuccess) return e;
+  return set_smem<U_DWF, 2, 128>();
 }
 
 void launch_umma_forward(const Step& s, const UmmaMaps& m, const UmmaTuning& tu, int num_sms,
@@ -924,8 +941,14 @@ void launch_umma_forward(const Step& s, const UmmaMaps& m, const UmmaTuning& tu,
   UmmaArgs g = base_args(tu);   // S = Xb Wb: lanes = batch rows, columns = classes
   const int cg = fwd_cg(s.B, (tu.cg_mask & 1) ? 2 : 1);
   g.mt = ((s.B + BM - 1) / BM + cg - 1) / cg;
-  g.nt = s.Cp / BN;
-  const int units = umma_forward_grid(s.B, s.Cp, num_sms, cg) / cg;
+  const int bn = umma_tile_width(tu, cg);
+  g.nt = s.Cp / bn;
+  const int units = umma_forward_grid(s.B, s.Cp, num_sms, cg, bn) / cg;
+  if (bn == 128) {              // narrow tiles: more units for shards that do not fill the pairs
+    set_segments(g, s.x3 != 0, (s.D + BK - 1) / BK, kSegHi, kSegLo, x3_segments(), s.D, s.Cp);
+    launch_k<U_FWD, 2, 128>(units, m.xb_k, m.wb_mn, m.wb_mn, s, g, st);
+    return;
+  }
   if (s.D <= 512 && (tu.debug_flags & 4) && cg == 2 && !s.x3) {
     // opt-in: Xb row tiles resident in both CTAs of a pair, only the weight halves stream
     g.kb_total = (s.D + BK - 1) / BK;
@@ -951,11 +974,13 @@ void launch_umma_bwdg(const Step& s, const UmmaMaps& m, const UmmaTuning& tu, in
   UmmaArgs g = base_args(tu);   // recompute S^T -> G'' (bf16) + q_part: lanes = classes
   const int cg = (tu.cg_mask & 2) ? 2 : 1;
   g.mt = s.Cp / (BM * cg);
-  g.nt = (s.B + BN - 1) / BN;
+  const int bn = umma_tile_width(tu, cg);
+  g.nt = (s.B + bn - 1) / bn;
   // A = weights, B = embeddings: the same plane pairs with the roles swapped
   set_segments(g, s.x3 != 0, (s.D + BK - 1) / BK, kSegLo, kSegHi, x3_segments(), s.Cp, s.D);
   const int units = min(g.mt * g.nt, num_sms / cg);
-  if (cg == 2 && (tu.debug_flags & 8)) launch_k<U_BWDG1, 2>(units, m.wb_mn, m.xb_k, m.g_st, s, g, st);
+  if (bn == 128) launch_k<U_BWDG, 2, 128>(units, m.wb_mn, m.xb_mn, m.g_st, s, g, st);   // X box: 64 rows per CTA
+  else if (cg == 2 && (tu.debug_flags & 8)) launch_k<U_BWDG1, 2>(units, m.wb_mn, m.xb_k, m.g_st, s, g, st);
   else if (cg == 2) launch_k<U_BWDG, 2>(units, m.wb_mn, m.xb_k, m.g_st, s, g, st);
   else launch_k<U_BWDG, 1>(units, m.wb_mn, m.xb_k256, m.g_st, s, g, st);
 }
@@ -965,10 +990,17 @@ void launch_umma_dw(const Step& s, const UmmaMaps& m, const UmmaTuning& tu, int 
   UmmaArgs g = base_args(tu);   // dW^T = G''^T Xb - correction: lanes = classes, columns = d
   const int cg = (tu.cg_mask & 4) ? 2 : 1;
   g.mt = s.Cp / (BM * cg);
-  g.nt = (s.D + BN - 1) / BN;
+  const int bn = umma_tile_width(tu, cg);
+  g.nt = (s.D + bn - 1) / bn;
   set_segments(g, s.x3 != 0, (s.B + BK - 1) / BK, kSegG, kSegO, x3_segments() < 5 ? x3_segments() : 5,
                s.Cp, s.D);
   const int units = min(g.mt * g.nt, num_sms / cg);
+  if (bn == 128) {
+    if (s.opt.kind != 0) launch_k<U_DWOPT, 2, 128>(units, m.g_mn, m.xb_mn, m.wb_box, s, g, st);
+    else if (s.x3) launch_k<U_DWF, 2, 128>(units, m.g_mn, m.xb_mn, m.wb_box, s, g, st);
+    else launch_k<U_DW, 2, 128>(units, m.g_mn, m.xb_mn, m.wb_box, s, g, st);
+    return;
+  }
   if (s.opt.kind == 0 && s.x3) {
     if (cg == 2) launch_k<U_DWF, 2>(units, m.g_mn, m.xb_mn, m.wb_box, s, g, st);
     else launch_k<U_DWF, 1>(units, m.g_mn, m.xb_mn, m.wb_box, s, g, st);
