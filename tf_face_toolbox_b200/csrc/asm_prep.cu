@@ -145,10 +145,19 @@ void launch_prep(const Step& s, const void* labels, int label_bytes, cudaStream_
   // cfg 3 (263.9 MB): 32x8/U=4 51.7 us (5.1 TB/s), 16x16/U=8 51.7, 32x8/U=8 53.2,
   // 32x8/U=16 59.8, 32x8/U=32 94, 32x8/U=2 65, 128x2/U=16 73: occupancy beats unroll depth,
   // and wider per-block column spans do not help.  ASM_PREP_SHAPE selects the alternatives.
-  static int shape = -1;
+  static int shape = -1, small_auto = -1;
   if (shape < 0) {
     const char* e = getenv("ASM_PREP_SHAPE");
     shape = e ? atoi(e) : 0;
+    // ASM_PREP_AUTO=1 (opt-in until measured): shards below 32 k classes have too few 64-column
+    // blocks to fill the SMs, so they take the 16x16 shape (32 columns per block, twice the
+    // blocks, half the dependent trips) -- DESIGN.md section 9.
+    e = getenv("ASM_PREP_AUTO");
+    small_auto = (e && atoi(e) != 0) ? 1 : 0;
+  }
+  if (shape == 0 && small_auto && s.Cp <= 32768) {
+    launch_prep_t<16, 16, 8>(s, labels, label_bytes, st);
+    return;
   }
   if (shape == 1) launch_prep_t<32, 8, 16>(s, labels, label_bytes, st);
   else if (shape == 2) launch_prep_t<16, 16, 8>(s, labels, label_bytes, st);
