@@ -404,11 +404,14 @@ def run_ours(args, cfg):
             continue                          # graph steps own their static input buffers
         dev_step = paths[name]
         src = head_nv if name == "nvlink" else (head if world > 1 else None)
+        ls = os.environ.get("BENCH_LOSS_STREAM", "0") == "1"      # opt-in A/B of the read-back stream
         if src is not None:
-            runner = HostPipelinedStep(lambda X, y, _h=src: _h.step(X, y, LAMBDA), b_local, D, dev)
+            runner = HostPipelinedStep(lambda X, y, _h=src: _h.step(X, y, LAMBDA), b_local, D, dev,
+                                       loss_stream=ls)
         else:
             runner = HostPipelinedStep(lambda X, y: (lambda o: (o[0], o[2], o[3]))(
-                asoftmax_head(X, y, Cn, M_MARGIN, LAMBDA, weights=Wd, mode=mode)), b_local, D, dev)
+                asoftmax_head(X, y, Cn, M_MARGIN, LAMBDA, weights=Wd, mode=mode)), b_local, D, dev,
+                loss_stream=ls)
 
         def fn(_r=runner):
             return _r.submit(Xh, yh)

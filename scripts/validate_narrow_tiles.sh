@@ -21,3 +21,7 @@ print("BN=$bn N=$N", round(d["value"]), "samples/s", round(d["ms_per_step"] * 10
       {k["kernel"][:6]: round(k["ms"] * 1000, 1) for k in d.get("kernels", [])})
 PY
 done
+
+# Other opt-ins waiting for a measurement (same A/B harness):
+#   bash scripts/ab_bench.sh BENCH_LOSS_STREAM "0 1"        # e2e: loss read-back on its own stream
+#   ASM_PREP_AUTO=1 at N = 4 / 8                            # norm-kernel shape for small shards
