@@ -25,3 +25,5 @@ done
 # Other opt-ins waiting for a measurement (same A/B harness):
 #   bash scripts/ab_bench.sh BENCH_LOSS_STREAM "0 1"        # e2e: loss read-back on its own stream
 #   ASM_PREP_AUTO=1 at N = 4 / 8                            # norm-kernel shape for small shards
+#   ASM_OPT_STREAM=1 python scripts/bench_train_step.py     # streaming optimizer vs fused epilogue
+#   ASM_OPT_STREAM=1 python -m pytest tests -q -m gpu -k optimizer

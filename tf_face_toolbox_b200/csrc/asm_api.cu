@@ -26,6 +26,8 @@ struct asm_head {
   size_t dx_part_capacity = 0;   // floats
   UmmaMaps maps{};
   int maps_B = -1;
+  bool opt_stream = false;       // ASM_OPT_STREAM=1: dW kernel + streaming update instead of the fused epilogue (opt-in)
+  float* dw_scratch = nullptr;   // [D, C_local] fp32, allocated on first use of opt_stream
   bool defer_loss = true;        // ASM_DEFER_LOSS=0: combine reduces the loss itself (A/B knob)
   bool tc = false;               // tcgen05 kernels (bf16 mode, or fp32 mode through bf16 planes)
   UmmaTuning tune{8192, 1024, 2048, 15, 0, 0};   // CTA pairs on all four kernels (ASM_UMMA_CG=0: single-CTA)
@@ -285,7 +287,22 @@ int run_backward(asm_head* h, const float* stats_all, int n_shards, float* loss_
       sx = h->side;
     }
     mark(h, "dw_gemm", stream);
-    if (tc) launch_umma_dw(s, h->maps, h->tune, h->num_sms, stream);
+    if (tc && s.opt.kind != 0 && h->opt_stream) {
+      // opt-in alternative to the fused epilogue: plain dW into a scratch buffer, then one
+      // streaming pass over (dW, W, state)
+      if (!h->dw_scratch &&
+          cudaMalloc(&h->dw_scratch, (size_t)s.D * h->cfg.C_local * sizeof(float)) != cudaSuccess) {
+        cudaGetLastError();
+        h->dw_scratch = nullptr;
+        return fail(h, ASM_ERR_ALLOC, "cudaMalloc(dW scratch for ASM_OPT_STREAM)%s", "");
+      }
+      Step t = s;
+      t.opt.kind = 0;
+      t.dW = h->dw_scratch;
+      launch_umma_dw(t, h->maps, h->tune, h->num_sms, stream);
+      mark(h, "opt_stream", stream);
+      launch_opt_stream(s, h->dw_scratch, stream);
+    } else if (tc) launch_umma_dw(s, h->maps, h->tune, h->num_sms, stream);
     else launch_simt_dw(s, stream);
     mark(h, "dx_gemm", sx);
     if (tc) launch_umma_dx(s, h->maps, h->tune, h->num_sms, sx);
@@ -348,6 +365,7 @@ int asm_create(asm_head** out, const asm_config* cfg) {
   if ((e = getenv("ASM_NO_OVERLAP")) && atoi(e)) h->overlap = false;
   if ((e = getenv("ASM_PDL"))) h->pdl = atoi(e) != 0;
   if ((e = getenv("ASM_DEFER_LOSS"))) h->defer_loss = atoi(e) != 0;
+  if ((e = getenv("ASM_OPT_STREAM"))) h->opt_stream = atoi(e) != 0;
   if (cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess) {
@@ -421,6 +439,7 @@ int asm_create(asm_head** out, const asm_config* cfg) {
 int asm_destroy(asm_head* h) {
   if (!h) return ASM_ERR_INVALID_ARG;
   if (h->ws) cudaFree(h->ws);
+  if (h->dw_scratch) cudaFree(h->dw_scratch);
   if (h->side) cudaStreamDestroy(h->side);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);

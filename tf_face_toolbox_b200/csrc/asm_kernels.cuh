@@ -161,6 +161,8 @@ void launch_combine_global(const Step& s, const float* stats_all, int n_shards, 
 void launch_combine_fused(const Step& s, cudaStream_t st);
 // dX = sum_z dx_part[z] + r_i x_i
 void launch_dx_finish(const Step& s, cudaStream_t st);
+// streaming classifier update from a dW buffer (alternative to the fused dW epilogue)
+void launch_opt_stream(const Step& s, const float* dW, cudaStream_t st);
 
 // fp32 (CUDA-core) contractions with fused epilogues
 void launch_simt_forward(const Step& s, cudaStream_t st);

@@ -362,4 +362,59 @@ void launch_dx_finish(const Step& s, cudaStream_t st) {
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// opt_stream: the classifier update as ONE streaming pass over (dW, W, state) after the plain
+// dW kernel -- the alternative to the fused dW epilogue (ASM_OPT_STREAM=1, DESIGN.md section 9
+// item 4).  Same opt_apply arithmetic; fully sequential 16-byte accesses.
+// ---------------------------------------------------------------------------------------
+template <int V>
+__global__ void __launch_bounds__(256) opt_stream_kernel(const float* __restrict__ dW, float* W, float* s0,
+                                                         float* s1, size_t n, OptParams op) {
+  pdl_trigger();
+  pdl_wait();
+  const size_t stride = (size_t)gridDim.x * blockDim.x * V;
+  for (size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * V; i < n; i += stride) {
+    float g[V], w[V], a[V], b[V];
+    if (V == 4) {
+      const float4 gv = __ldcs(reinterpret_cast<const float4*>(dW + i));
+      const float4 wv = *reinterpret_cast<const float4*>(W + i);
+      const float4 av = *reinterpret_cast<const float4*>(s0 + i);
+      const float4 bv = op.kind == 2 ? *reinterpret_cast<const float4*>(s1 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      g[0] = gv.x; g[1] = gv.y; g[2] = gv.z; g[3] = gv.w;
+      w[0] = wv.x; w[1] = wv.y; w[2] = wv.z; w[3] = wv.w;
+      a[0] = av.x; a[1] = av.y; a[2] = av.z; a[3] = av.w;
+      b[0] = bv.x; b[1] = bv.y; b[2] = bv.z; b[3] = bv.w;
+    } else {
+      g[0] = dW[i]; w[0] = W[i]; a[0] = s0[i]; b[0] = op.kind == 2 ? s1[i] : 0.f;
+    }
+#pragma unroll
+    for (int v = 0; v < V; ++v) opt_apply(op, g[v], w[v], a[v], b[v]);
+    if (V == 4) {
+      *reinterpret_cast<float4*>(W + i) = make_float4(w[0], w[1], w[2], w[3]);
+      *reinterpret_cast<float4*>(s0 + i) = make_float4(a[0], a[1], a[2], a[3]);
+      if (op.kind == 2) *reinterpret_cast<float4*>(s1 + i) = make_float4(b[0], b[1], b[2], b[3]);
+    } else {
+      W[i] = w[0]; s0[i] = a[0];
+      if (op.kind == 2) s1[i] = b[0];
+    }
+  }
+}
+
+void launch_opt_stream(const Step& s, const float* dW, cudaStream_t st) {
+  const size_t n = (size_t)s.D * s.C;
+  const uintptr_t al = reinterpret_cast<uintptr_t>(dW) | reinterpret_cast<uintptr_t>(s.Wmut) |
+                       reinterpret_cast<uintptr_t>(s.opt_s0) | reinterpret_cast<uintptr_t>(s.opt_s1);
+  if (n % 4 == 0 && (al & 15) == 0) {
+    size_t blocks = (n / 4 + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    launch_pdl(opt_stream_kernel<4>, dim3((unsigned)blocks), dim3(256), 0, st, false, 1, dW, s.Wmut, s.opt_s0,
+               s.opt_s1, n, s.opt);
+  } else {
+    size_t blocks = (n + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    launch_pdl(opt_stream_kernel<1>, dim3((unsigned)blocks), dim3(256), 0, st, false, 1, dW, s.Wmut, s.opt_s0,
+               s.opt_s1, n, s.opt);
+  }
+}
+
 }  // namespace asmh
