@@ -46,7 +46,8 @@ typedef enum {
   ASM_ERR_CUDA = -2,          /* a CUDA runtime / driver call failed (see asm_last_error) */
   ASM_ERR_NO_DEVICE = -3,     /* no sm_100 device: there is NO CPU fallback */
   ASM_ERR_LABEL_RANGE = -4,   /* a label was outside [0, C_total) (asm_check_labels) */
-  ASM_ERR_ALLOC = -5
+  ASM_ERR_ALLOC = -5,
+  ASM_ERR_PEER_TIMEOUT = -6   /* NVLink transport: a peer did not publish in time (asm_p2p_status) */
 } asm_status;
 
 enum { ASM_MODE_FP32 = 0, ASM_MODE_BF16 = 1 };
@@ -180,14 +181,22 @@ int asm_center_loss(const float* X, int32_t B, int32_t D, const void* labels, in
  *                   rank passes the same b_local; global batch = b_local * world);
  *                   W / dW: this shard's [D, C_local]; loss_out: global mean loss;
  *                   dX_local [b_local, D]: the complete gradient of this rank's rows.
- * Asynchronous on cuda_stream and capturable into a CUDA graph.  A peer that never arrives
- * makes the waiting kernel trap after ~2 s (reported as a CUDA error) instead of hanging.
+ * Asynchronous on cuda_stream and capturable into a CUDA graph (the step counter lives on the
+ * device).  Seven kernel launches per step, none of them transport-only: the norm kernel publishes
+ * and gathers the rows, the statistics exchange rides in the combine kernel, the dX exchange in
+ * the dX-finish kernel.  Ranks must stay in lock-step (every rank calls asm_step_p2p once per
+ * step).  A wait for a peer gives up after the configured time (default 60 s, env
+ * ASM_P2P_TIMEOUT_MS or asm_p2p_set_timeout; 0 = wait for ever): nothing traps and the CUDA
+ * context stays usable, but that step's results are undefined and asm_p2p_status -- which
+ * synchronises the stream -- returns ASM_ERR_PEER_TIMEOUT from then on.
  */
 size_t asm_p2p_bytes(const asm_config* cfg);
 int asm_p2p_attach(asm_head* h, void* const* peer_bases);
 int asm_step_p2p(asm_head* h, const float* X_local, int32_t b_local, const void* labels_local,
                  int32_t label_bytes, const float* W, float lambda, float* loss_out,
                  float* dX_local, float* dW, void* cuda_stream);
+int asm_p2p_set_timeout(asm_head* h, int32_t milliseconds);
+int asm_p2p_status(asm_head* h, void* cuda_stream);
 
 /* CUDA-graph support.  Kernel arguments are frozen when a step is captured into a graph, so
  * lambda (which anneals per step) can instead be read from a caller-owned DEVICE float:

@@ -142,6 +142,85 @@ def asoftmax_head(X, W, y, m: int = 4, lam: float = 0.0, dtype=np.float64) -> He
     return HeadResult(loss, f, dX, dW, n, c, t, psi, row_max, np.log(Z))
 
 
+@dataclass
+class StreamedResult:
+    loss: float
+    dX: np.ndarray          # [B, D]
+    dW: dict                # (lo, hi) -> dW[:, lo:hi] for every requested class range
+    row_max: np.ndarray
+    row_logz: np.ndarray
+
+
+def asoftmax_head_streamed(X, W, y, m: int = 4, lam: float = 0.0, chunk: int = 16384,
+                           dw_ranges=(), dtype=np.float64) -> StreamedResult:
+    """The same head evaluated in class chunks, never holding a [B, C] matrix: for the
+    BASELINE shapes whose logits do not fit in host memory (config 4: 1024 x 1,000,000) or are
+    slow to check in one piece (config 5: 2048 x 85,742).  Pass 1 keeps an online (max, sum-exp)
+    per row; pass 2 rebuilds each chunk's G' from it and accumulates dX; dW is produced only for
+    the class ranges asked for.  Same formulas as asoftmax_head (checked equal in
+    tests/test_oracle.py); `dtype` is the matmul precision (float32 halves the time, the
+    statistics stay float64)."""
+    X64 = np.asarray(X, dtype=np.float64)
+    Xc = X64.astype(dtype)
+    y = np.asarray(y).astype(np.int64)
+    B, D = Xc.shape
+    C = W.shape[1]
+    if y.min() < 0 or y.max() >= C:
+        raise ValueError("label out of range")
+    n = np.sqrt((X64 * X64).sum(axis=1))
+    bounds = [(lo, min(C, lo + chunk)) for lo in range(0, C, chunk)]
+
+    def chunk_logits(lo, hi):
+        Wc = np.asarray(W[:, lo:hi], dtype=np.float64)
+        c = np.sqrt((Wc * Wc).sum(axis=0))
+        What = (Wc / c).astype(dtype)
+        return (Xc @ What).astype(np.float64), What, c
+
+    # target column first: t, psi, f_y (the target's own chunk is rebuilt in pass 2)
+    Wy = np.asarray(W[:, y], dtype=np.float64)                 # [D, B]
+    cy = np.sqrt((Wy * Wy).sum(axis=0))
+    s_y = np.einsum("bd,db->b", X64, Wy / cy)
+    t = np.clip(s_y / n, -1.0, 1.0)
+    psi, dpsi, _ = psi_kform(t, m)
+    f_y = (lam * s_y + n * psi) / (1.0 + lam)
+
+    M = np.full(B, -np.inf)
+    Z = np.zeros(B)
+    for lo, hi in bounds:                                      # pass 1: online log-sum-exp
+        f, _, _ = chunk_logits(lo, hi)
+        own = np.nonzero((y >= lo) & (y < hi))[0]
+        f[own, y[own] - lo] = f_y[own]
+        mc = f.max(axis=1)
+        Mn = np.maximum(M, mc)
+        Z = Z * np.exp(M - Mn) + np.exp(f - Mn[:, None]).sum(axis=1)
+        M = Mn
+    lse = M + np.log(Z)
+    loss = float(np.mean(lse - f_y))
+
+    dX = np.zeros((B, D))
+    dW = {}
+    for lo, hi in bounds:                                      # pass 2: gradients
+        S, What, c = chunk_logits(lo, hi)
+        own = np.nonzero((y >= lo) & (y < hi))[0]
+        f = S.copy()
+        f[own, y[own] - lo] = f_y[own]
+        Gp = np.exp(f - lse[:, None]) / B
+        g_y = Gp[own, y[own] - lo] - 1.0 / B
+        Gp[own, y[own] - lo] = g_y * (lam + dpsi[own]) / (1.0 + lam)
+        dX += (Gp.astype(dtype) @ What.T).astype(np.float64)
+        dX[own] += (g_y * (psi[own] - t[own] * dpsi[own]) / ((1.0 + lam) * n[own]))[:, None] * X64[own]
+        for (rlo, rhi) in dw_ranges:
+            a, b = max(lo, rlo), min(hi, rhi)
+            if a >= b:
+                continue
+            sl = slice(a - lo, b - lo)
+            dWhat = (Xc.T @ Gp[:, sl].astype(dtype)).astype(np.float64)
+            q = (Gp[:, sl] * S[:, sl]).sum(axis=0)
+            dW.setdefault((rlo, rhi), np.zeros((D, rhi - rlo)))[:, a - rlo:b - rlo] = \
+                (dWhat - What[:, sl].astype(np.float64) * q) / c[sl]
+    return StreamedResult(loss, dX, dW, M, np.log(Z))
+
+
 def asoftmax_loss_only(X, W, y, m=4, lam=0.0, dtype=np.float64) -> float:
     """Loss without gradients (for finite differences)."""
     X = np.asarray(X, dtype=dtype)

@@ -3,6 +3,9 @@ import sys
 
 import pytest
 
+# one hardware queue per stream for the single-GPU multi-rank transport tests (read at CUDA init)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

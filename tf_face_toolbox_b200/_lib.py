@@ -11,7 +11,9 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libasoftmax_b200.so")
+# ASM_B200_LIB selects another build of the same library (the -DASM_BRINGUP one under lib/bringup/,
+# for kernel bring-up experiments only; bench.py reports any ASM_* variable in its JSON line)
+LIB_PATH = os.environ.get("ASM_B200_LIB") or os.path.join(_HERE, "lib", "libasoftmax_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 ASM_OK = 0
@@ -20,6 +22,7 @@ ASM_ERR_CUDA = -2
 ASM_ERR_NO_DEVICE = -3
 ASM_ERR_LABEL_RANGE = -4
 ASM_ERR_ALLOC = -5
+ASM_ERR_PEER_TIMEOUT = -6
 MODE_FP32, MODE_BF16 = 0, 1
 MODES = {"fp32": MODE_FP32, "bf16": MODE_BF16}
 
@@ -68,6 +71,8 @@ SYMBOLS = {
     "asm_p2p_bytes": (C.c_size_t, [C.POINTER(AsmConfig)]),
     "asm_p2p_attach": (C.c_int, [_P, C.POINTER(C.c_void_p)]),
     "asm_step_p2p": (C.c_int, [_P, _P, C.c_int32, _P, C.c_int32, _P, C.c_float, _P, _P, _P, _P]),
+    "asm_p2p_set_timeout": (C.c_int, [_P, C.c_int32]),
+    "asm_p2p_status": (C.c_int, [_P, _P]),
     "asm_set_lambda_device": (C.c_int, [_P, _P]),
     "asm_set_profiling": (C.c_int, [_P, C.c_int]),
     "asm_get_profile": (C.c_int, [_P, C.c_int32, _P, _P]),

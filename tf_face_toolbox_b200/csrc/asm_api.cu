@@ -30,7 +30,7 @@ struct asm_head {
   float* dw_scratch = nullptr;   // [D, C_local] fp32, allocated on first use of opt_stream
   bool defer_loss = true;        // ASM_DEFER_LOSS=0: combine reduces the loss itself (A/B knob)
   bool tc = false;               // tcgen05 kernels (bf16 mode, or fp32 mode through bf16 planes)
-  UmmaTuning tune{8192, 1024, 2048, 15, 0, 0};   // CTA pairs on all four kernels (ASM_UMMA_CG=0: single-CTA)
+  UmmaTuning tune{8192, 1024, 2048, 15, 0, 0, 1, 1, 3};   // CTA pairs on all four kernels (ASM_UMMA_CG=0: single-CTA)
   bool fwd_valid = false;
   // dX branch of the backward (DX + dx_finish) runs on a second stream so that it fills the
   // SMs the DW kernel's tail leaves idle; both only depend on G'' from the BWDG kernel
@@ -42,8 +42,6 @@ struct asm_head {
   P2P p2p{};
   bool p2p_ready = false;
   float* Xg = nullptr;           // [B_max, D] gathered embeddings
-  int* yg = nullptr;             // [B_max]    gathered labels
-  float* stats_all = nullptr;    // [world, 3, B_max]
   size_t l2_persist_bytes = 0;   // ASM_L2_PERSIST_MB: pin the bf16 weight copy in L2
   cudaStream_t l2_stream = nullptr;
   bool l2_set = false;
@@ -64,7 +62,7 @@ size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct Layout {
   size_t ylocal, flags, n, inv_n, inv_c, tgt_s, tgt_f, part, stats_local, lse, negoff, gtarget, rcoef, rowloss, counter,
-      q_part, G, dx_part, Xb, Wb, Xg, yg, stats_all, step_dev, total;
+      q_part, G, dx_part, Xb, Wb, Xg, step_dev, total;
   int Cp, NT, MT;
   size_t dx_capacity;
 };
@@ -135,8 +133,6 @@ Layout make_layout(const asm_config& c, int num_sms) {
   }
   if (c.world > 1) {
     L.Xg = take(B * D * 4);
-    L.yg = take(B * 4);
-    L.stats_all = take((size_t)c.world * 3 * B * 4);
     L.step_dev = take(256);
   }
   L.total = off;
@@ -180,7 +176,7 @@ int check_launch(asm_head* h, const char* what) {
 // forward half up to stats_local; shared by every entry point
 int run_forward(asm_head* h, const float* X, int B, const void* labels, int label_bytes,
                 const float* W, float lambda, float* logits, bool want_local_stats,
-                cudaStream_t stream) {
+                cudaStream_t stream, const P2P* tp = nullptr) {
   if (!h) return ASM_ERR_INVALID_ARG;
   if (!X || !labels || !W) return fail(h, ASM_ERR_INVALID_ARG, "null input pointer%s", "");
   if (B <= 0 || B > h->cfg.B_max) return fail(h, ASM_ERR_INVALID_ARG, "B out of range%s", "");
@@ -194,6 +190,7 @@ int run_forward(asm_head* h, const float* X, int B, const void* labels, int labe
   s.X = X;
   s.W = W;
   s.logits = logits;
+  s.l2_hints = (h->tune.l2_hints & 1) ? 1 : 0;
   s.MT = h->tc ? umma_q_parts(B, umma_tile_width(h->tune, (h->tune.cg_mask & 2) ? 2 : 1))
                : (B + kRowTileHost - 1) / kRowTileHost;
   h->launches = 0;
@@ -241,7 +238,7 @@ int run_forward(asm_head* h, const float* X, int B, const void* labels, int labe
   }
   while (s.KS > 1 && (size_t)s.KS * B * s.D > h->dx_part_capacity) --s.KS;
   mark(h, "prep_norms", stream);
-  launch_prep(s, labels, label_bytes, stream);
+  launch_prep(s, labels, label_bytes, stream, tp);
   mark(h, "fwd_logits_stats", stream);
   if (h->tc) launch_umma_forward(s, h->maps, h->tune, h->num_sms, stream);
   else launch_simt_forward(s, stream);
@@ -256,7 +253,7 @@ int run_forward(asm_head* h, const float* X, int B, const void* labels, int labe
 }
 
 int run_backward(asm_head* h, const float* stats_all, int n_shards, float* loss_out,
-                 float* dX, float* dW, bool grads, cudaStream_t stream) {
+                 float* dX, float* dW, bool grads, cudaStream_t stream, const P2P* tp = nullptr) {
   Step& s = h->st;
   s.loss = loss_out;
   s.dX = dX;
@@ -264,7 +261,10 @@ int run_backward(asm_head* h, const float* stats_all, int n_shards, float* loss_
   s.Wmut = const_cast<float*>(s.W);       // only written when an optimizer is armed
   const bool tc = h->tc;
   s.defer_loss = (grads && tc && h->defer_loss) ? 1 : 0;   // the tcgen05 dX kernel reduces the loss
-  if (stats_all) {
+  if (tp) {
+    mark(h, "combine_exchange", stream);
+    launch_combine_p2p(s, *tp, stream);
+  } else if (stats_all) {
     // profiling: the gap between the two halves is the host-side statistics all-gather
     if (h->profiling && h->n_marks > 0 && h->n_marks < asm_head::kMaxMarks)
       h->mark_name[h->n_marks++] = "stats_exchange_host";
@@ -278,14 +278,27 @@ int run_backward(asm_head* h, const float* stats_all, int n_shards, float* loss_
     mark(h, "bwd_recompute_g", stream);
     if (tc) launch_umma_bwdg(s, h->maps, h->tune, h->num_sms, stream);
     else launch_simt_bwdg(s, stream);
+    // The CUDA-core dX kernel reads the fp32 master weights, which a fused optimizer rewrites in
+    // the dW kernel: in that combination dX runs first, on the same stream (the tcgen05 kernels
+    // read the bf16 copy, which the update never touches, so they may overlap).
+    const bool dx_first = !tc && s.opt.kind != 0;
     // the per-kernel profile needs one stream; otherwise fork the dX branch
-    const bool fork = h->overlap && !h->profiling && h->side != nullptr;
+    const bool fork = h->overlap && !h->profiling && h->side != nullptr && !dx_first;
     cudaStream_t sx = stream;
     if (fork) {
       cudaEventRecord(h->ev_fork, stream);
       cudaStreamWaitEvent(h->side, h->ev_fork, 0);
       sx = h->side;
     }
+    auto run_dx = [&]() {
+      mark(h, "dx_gemm", sx);
+      if (tc) launch_umma_dx(s, h->maps, h->tune, h->num_sms, sx);
+      else launch_simt_dx(s, sx);
+      mark(h, tp ? "dx_finish_exchange" : "dx_finish", sx);
+      if (tp) launch_dx_finish_p2p(s, *tp, sx);
+      else launch_dx_finish(s, sx);
+    };
+    if (dx_first) run_dx();
     mark(h, "dw_gemm", stream);
     if (tc && s.opt.kind != 0 && h->opt_stream) {
       // opt-in alternative to the fused epilogue: plain dW into a scratch buffer, then one
@@ -302,13 +315,11 @@ int run_backward(asm_head* h, const float* stats_all, int n_shards, float* loss_
       launch_umma_dw(t, h->maps, h->tune, h->num_sms, stream);
       mark(h, "opt_stream", stream);
       launch_opt_stream(s, h->dw_scratch, stream);
-    } else if (tc) launch_umma_dw(s, h->maps, h->tune, h->num_sms, stream);
-    else launch_simt_dw(s, stream);
-    mark(h, "dx_gemm", sx);
-    if (tc) launch_umma_dx(s, h->maps, h->tune, h->num_sms, sx);
-    else launch_simt_dx(s, sx);
-    mark(h, "dx_finish", sx);
-    launch_dx_finish(s, sx);
+    } else if (tc) {
+      if (s.opt.kind == 0 && !s.x3 && h->tune.dw_tma) umma_build_dw_maps(&h->maps, s);
+      launch_umma_dw(s, h->maps, h->tune, h->num_sms, stream);
+    } else launch_simt_dw(s, stream);
+    if (!dx_first) run_dx();
     if (fork) {
       cudaEventRecord(h->ev_join, h->side);
       cudaStreamWaitEvent(stream, h->ev_join, 0);
@@ -359,7 +370,19 @@ int asm_create(asm_head** out, const asm_config* cfg) {
   if ((e = getenv("ASM_UMMA_MN_LBO"))) h->tune.mn_lbo = (uint32_t)atoi(e);
   if ((e = getenv("ASM_UMMA_MN_SBO"))) h->tune.mn_sbo = (uint32_t)atoi(e);
   if ((e = getenv("ASM_UMMA_MN_KSTEP"))) h->tune.mn_kstep = (uint32_t)atoi(e);
-  if ((e = getenv("ASM_UMMA_DEBUG"))) h->tune.debug_flags = (uint32_t)atoi(e);
+  if ((e = getenv("ASM_UMMA_DEBUG")) && atoi(e) != 0) {
+#ifdef ASM_BRINGUP
+    h->tune.debug_flags = (uint32_t)atoi(e);
+#else
+    // work-skipping bring-up bits do not exist in the product build: refuse rather than ignore
+    delete h;
+    return fail(nullptr, ASM_ERR_INVALID_ARG,
+                "ASM_UMMA_DEBUG is set but this library was built without -DASM_BRINGUP%s", "");
+#endif
+  }
+  if ((e = getenv("ASM_L2_ORDER"))) h->tune.l2_order = atoi(e) != 0;
+  if ((e = getenv("ASM_DW_TMA"))) h->tune.dw_tma = atoi(e) != 0;
+  if ((e = getenv("ASM_L2_HINTS"))) h->tune.l2_hints = (uint32_t)atoi(e);
   if ((e = getenv("ASM_UMMA_CG"))) h->tune.cg_mask = (uint32_t)atoi(e);
   if ((e = getenv("ASM_UMMA_BN"))) h->tune.bn = (uint32_t)atoi(e);   // 128: narrow tiles (not validated on hardware yet)
   if ((e = getenv("ASM_NO_OVERLAP")) && atoi(e)) h->overlap = false;
@@ -427,9 +450,9 @@ int asm_create(asm_head** out, const asm_config* cfg) {
   }
   if (cfg->world > 1) {
     h->Xg = (float*)(w + L.Xg);
-    h->yg = (int*)(w + L.yg);
-    h->stats_all = (float*)(w + L.stats_all);
-    h->p2p.step_dev = (unsigned*)(w + L.step_dev);
+    h->p2p.step_dev = (unsigned*)(w + L.step_dev);     // zeroed with the workspace
+    h->p2p.err_dev = h->p2p.step_dev + 1;
+    h->p2p.tickets = h->p2p.step_dev + 2;
   }
   h->Cp = L.Cp;
   *out = h;
@@ -541,6 +564,13 @@ int asm_p2p_attach(asm_head* h, void* const* peer_bases) {
     if (!peer_bases[r]) return fail(h, ASM_ERR_INVALID_ARG, "peer base is NULL%s", "");
     p.base[r] = (char*)peer_bases[r];
   }
+  // per-wait limit: ASM_P2P_TIMEOUT_MS (default 60 s; 0 = wait for ever), see asm_p2p_set_timeout
+  const char* e = getenv("ASM_P2P_TIMEOUT_MS");
+  p.timeout_ns = (unsigned long long)(e ? atoll(e) : 60000ll) * 1000000ull;
+  e = getenv("ASM_P2P_WAITERS");        // several ranks on one GPU (tests): keep the spinning blocks few
+  p.waiters = e ? atoi(e) : 1 << 20;
+  if (p.waiters < 1) p.waiters = 1;
+  p2p_preload_kernels();
   h->p2p_ready = true;
   return ASM_OK;
 }
@@ -559,35 +589,36 @@ int asm_step_p2p(asm_head* h, const float* X_local, int32_t b_local, const void*
     return fail(h, ASM_ERR_INVALID_ARG, "b_local out of range%s", "");
   cudaStream_t stream = (cudaStream_t)cuda_stream;
   p.b_local = b_local;
+  p.x_local = X_local;
+  p.y_local = labels_local;
+  p.y_bytes = label_bytes;
+  p.dx_local = dX_local;
+  p.Xg = h->Xg;
   const int B = b_local * p.world;
-  Step& s = h->st;
-  // phase 0: publish my rows, gather everybody's
-  launch_p2p_pack(p, X_local, labels_local, label_bytes, s.D, stream);
-  launch_p2p_signal(p, 0, 1, stream);
-  launch_p2p_gather_x(p, h->Xg, h->yg, s.D, stream);
-  // forward on the gathered batch; this shard's statistics go to its symmetric block
-  float* ws_stats = s.stats_local;
-  s.par_step = p.step_dev;
-  s.stats_par_stride = (size_t)3 * p.B_max;
-  s.dx_par_stride = (size_t)p.B_max * s.D;
-  s.stats_local = p.st(p.rank, 0);
-  int rc = run_forward(h, h->Xg, B, h->yg, 4, W, lambda, nullptr, true, stream);
-  if (rc == ASM_OK) {
-    launch_p2p_signal(p, 1, 0, stream);
-    launch_p2p_gather_stats(p, h->stats_all, B, stream);
-    // backward; my dX contribution for all rows goes to the symmetric block, then every rank
-    // sums its own rows over the shards
-    rc = run_backward(h, h->stats_all, p.world, loss_out, p.dx(p.rank, 0), dW, true, stream);
-  }
-  if (rc == ASM_OK) {
-    launch_p2p_signal(p, 2, 0, stream);
-    launch_p2p_reduce_dx(p, dX_local, s.D, stream);
-    h->launches += 7;
-    rc = check_launch(h, "p2p launch");
-  }
-  s.stats_local = ws_stats;
-  s.par_step = nullptr;
+  // 7 launches, none of them transport-only: prep publishes this rank's rows and gathers
+  // everybody's, the statistics and dX exchanges ride in the combine and dx_finish kernels
+  int rc = run_forward(h, h->Xg, B, labels_local, label_bytes, W, lambda, nullptr, false, stream, &p);
+  if (rc == ASM_OK) rc = run_backward(h, nullptr, p.world, loss_out, nullptr, dW, true, stream, &p);
   return rc;
+}
+
+int asm_p2p_set_timeout(asm_head* h, int32_t milliseconds) {
+  if (!h || milliseconds < 0) return ASM_ERR_INVALID_ARG;
+  h->p2p.timeout_ns = (unsigned long long)milliseconds * 1000000ull;
+  return ASM_OK;
+}
+
+int asm_p2p_status(asm_head* h, void* cuda_stream) {
+  if (!h) return ASM_ERR_INVALID_ARG;
+  if (!h->p2p_ready) return ASM_OK;
+  unsigned code = 0;
+  CU_TRY(h, cudaMemcpyAsync(&code, h->p2p.err_dev, sizeof(code), cudaMemcpyDeviceToHost,
+                            (cudaStream_t)cuda_stream));
+  CU_TRY(h, cudaStreamSynchronize((cudaStream_t)cuda_stream));
+  if (code == 0) return ASM_OK;
+  snprintf(h->err, sizeof(h->err), "peer %u did not publish phase %u in time (ranks must stay in lock-step)",
+           code & 0xffu, (code >> 8) & 0xffu);
+  return ASM_ERR_PEER_TIMEOUT;
 }
 
 int asm_set_optimizer(asm_head* h, const asm_optimizer* opt, float* state0, float* state1) {

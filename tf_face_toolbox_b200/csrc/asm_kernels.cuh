@@ -39,9 +39,19 @@ constexpr int kMaxPeers = 8;
 constexpr int kFlagStride = 16;        // flag words per phase
 struct P2P {
   int rank, world, b_local, b_max, B_max, D;
-  unsigned* step_dev;                  // device step counter of this rank
+  unsigned* step_dev;                  // device counter: steps this rank has COMPLETED
+  unsigned* err_dev;                   // 0, or 0x80000000 | phase << 8 | src of the first wait that timed out
+  unsigned* tickets;                   // [4] last-block-done tickets of the producing kernels
+  int waiters;                         // blocks per exchange kernel that may wait for peers (ASM_P2P_WAITERS)
+  unsigned long long timeout_ns;       // per-wait limit (0 = wait for ever)
   char* base[kMaxPeers];               // every rank's symmetric block (own included)
   size_t off_x, off_y, off_st, off_dx, off_fl;
+  // per step (caller buffers of this rank)
+  const float* x_local;                // [b_local, D]
+  const void* y_local;                 // [b_local]
+  int y_bytes;
+  float* dx_local;                     // [b_local, D]
+  float* Xg;                           // [B, D] gathered embeddings (workspace; dx_finish reads them)
   __host__ __device__ float* x(int r, int par) const {
     return reinterpret_cast<float*>(base[r] + off_x) + (size_t)par * b_max * D;
   }
@@ -59,12 +69,6 @@ struct P2P {
   }
   __host__ __device__ unsigned* flags_local() const { return flags_of(rank); }
 };
-void launch_p2p_pack(const P2P& p, const float* X, const void* labels, int label_bytes, int D,
-                     cudaStream_t st);
-void launch_p2p_signal(const P2P& p, int phase, int bump, cudaStream_t st);
-void launch_p2p_gather_x(const P2P& p, float* Xg, int* yg, int D, cudaStream_t st);
-void launch_p2p_gather_stats(const P2P& p, float* stats_all, int B, cudaStream_t st);
-void launch_p2p_reduce_dx(const P2P& p, float* dX_local, int D, cudaStream_t st);
 
 // Launch with the programmatic-stream-serialization attribute when `pdl` is set (never while
 // the stream is being captured into a graph): the kernel may start while its predecessor
@@ -143,16 +147,19 @@ struct Step {
   float* Wmut;               // [D, C]  W, updated in place when opt.kind != 0
   float* opt_s0;             // [D, C]  momentum accumulator / adam m
   float* opt_s1;             // [D, C]  adam v
-  // P2P transport: outputs that live in the parity-double-buffered symmetric block are
-  // addressed as base + (*par_step & 1) * stride on the device (CUDA-graph friendly)
-  const unsigned* par_step;
+  int l2_hints;              // evict-first on single-use streams (the fp32 W read of the norm kernel)
   int pdl;                   // launch dependents programmatically (eager, non-captured streams)
   int defer_loss;            // the mean-loss reduction runs in an idle warp of the dX kernel, not in combine
-  size_t stats_par_stride, dx_par_stride;   // in floats
 };
 
-// prep: column norms of W (+ bf16 copy), row norms of X (+ bf16 copy), label localisation
-void launch_prep(const Step& s, const void* labels, int label_bytes, cudaStream_t st);
+// prep: column norms of W (+ bf16 copy), row norms of X (+ bf16 copy), label localisation.
+// With a transport (p != null): the same launch also publishes this rank's rows to its peers
+// and its embedding role gathers every rank's rows over NVLink as it normalises them.
+void launch_prep(const Step& s, const void* labels, int label_bytes, cudaStream_t st, const P2P* p = nullptr);
+// NVLink transport: statistics of this shard -> symmetric block, exchange, global combine (one launch)
+void launch_combine_p2p(const Step& s, const P2P& p, cudaStream_t st);
+// NVLink transport: dX contribution of this shard -> symmetric block, exchange, sum of this rank's rows (one launch)
+void launch_dx_finish_p2p(const Step& s, const P2P& p, cudaStream_t st);
 // combine per-tile (max,sumexp) partials into stats_local [3,B]
 void launch_combine_local(const Step& s, cudaStream_t st);
 // combine [n_shards,3,B] stats into lse / loss / target coefficients
@@ -163,6 +170,11 @@ void launch_combine_fused(const Step& s, cudaStream_t st);
 void launch_dx_finish(const Step& s, cudaStream_t st);
 // streaming classifier update from a dW buffer (alternative to the fused dW epilogue)
 void launch_opt_stream(const Step& s, const float* dW, cudaStream_t st);
+
+// force the lazy loading of every kernel the NVLink-transport step can launch (asm_p2p_attach)
+void p2p_preload_kernels();
+void prep_preload_kernels();
+void simt_preload_kernels();
 
 // fp32 (CUDA-core) contractions with fused epilogues
 void launch_simt_forward(const Step& s, cudaStream_t st);
@@ -175,12 +187,20 @@ int simt_dx_splits(int B, int D, int Cp);
 // bf16 (tcgen05 / TMEM / TMA) contractions with fused epilogues
 struct UmmaMaps {            // TMA descriptors over the bf16 workspace operands
   CUtensorMap xb_k, xb_k256, xb_mn, wb_mn, wb_mn32, wb_k, wb_k128, g_k, g_mn, g_st, wb_box;
+  // the caller's dW [D, C] fp32 seen as [D/2, 2C] (row pitch 8C bytes): even rows through a
+  // tensor of extent {C, D/2}, odd rows through one of extent {2C, D/2} at column offset C
+  CUtensorMap dw_even, dw_odd;
+  const void* dw_ptr;        // buffer the two maps above were encoded for (re-encoded when it changes)
+  int dw_ok;                 // 0: dW cannot be addressed by TMA (odd C, misaligned base): direct stores
 };
 struct UmmaTuning {          // MN-major shared-memory descriptor parameters (bytes)
   uint32_t mn_lbo, mn_sbo, mn_kstep;
   uint32_t cg_mask;          // CTA pairs (cta_group::2) per kernel: bit0 FWD, bit1 BWDG, bit2 DW, bit3 DX
   uint32_t debug_flags;      // bit0: skip epilogue math, bit1: DW without stores, bit2: X-resident forward variant (ASM_UMMA_DEBUG, bring-up only)
   uint32_t bn;               // tile width along N of FWD / BWDG / DW: 0 or 256 = default, 128 = narrow (ASM_UMMA_BN)
+  uint32_t l2_order;         // consecutive kernels sweep the classes in opposite directions (ASM_L2_ORDER=0 disables)
+  uint32_t dw_tma;           // dW leaves through shared memory + TMA stores (ASM_DW_TMA=0: direct stores)
+  uint32_t l2_hints;         // evict-first on single-use streams: bit0 the fp32 W read of the norm kernel, bit1 the dW stores (ASM_L2_HINTS)
 };
 struct UmmaArgs {
   int mt, nt, ks, kb_total, kb_per;
@@ -191,9 +211,16 @@ struct UmmaArgs {
   uint64_t desc_hi_k, desc_hi_mn;
   uint32_t kstep_mn;
   uint32_t debug_flags;
+  int rev;                   // class tiles (or, with kstride, K blocks) in descending order
+  int kstride;               // split-K: split z takes K blocks z, z + ks, ... instead of a contiguous range
+  int dw_tma;                // DW: staged TMA stores (maps D / E valid)
+  int dw_shift;              // DW: class offset of the odd-row boxes (2 when C % 4 == 2, else 0)
+  int store_evict_first;     // DW: the dW stores carry an evict-first L2 policy
 };
 cudaError_t umma_configure();
 bool umma_build_maps(UmmaMaps* m, const Step& s);
+// (re-)encode the dW store maps for this step's output buffer; sets m->dw_ok
+void umma_build_dw_maps(UmmaMaps* m, const Step& s);
 int umma_tile_width(const UmmaTuning& tu, int cg);
 int umma_forward_tiles(int B, int Cp, int num_sms, int cg, int bn = 256);
 int umma_forward_grid(int B, int Cp, int num_sms, int cg, int bn = 256);

@@ -4,6 +4,8 @@
 
 #include "asm_common.cuh"
 #include "asm_kernels.cuh"
+#include "asm_p2p.cuh"
+#include "asm_rows.cuh"
 
 namespace asmh {
 
@@ -16,17 +18,38 @@ namespace asmh {
 //     through shared memory into inv_c[j] = 1/||w_j||.  W is read exactly once.
 //   blocks [nwb, ...): X role. One warp per embedding row: n_i, 1/n_i, bf16 copy, and the
 //     label -> local-class-index translation with the range check.
+// With the NVLink transport (p.world > 1) the launch starts with npub PUBLISH blocks that copy
+// this rank's rows into its symmetric block and raise its phase-0 flag on every peer, and the X
+// role reads each row from the symmetric block of the rank that owns it (waiting for that
+// rank's flag) while it normalises it -- the all-gather of X costs no launch of its own, and
+// the W role, which depends on nobody, runs meanwhile.  Publish blocks come first in the grid
+// so that they are dispatched before any block that waits for a peer.
 // ---------------------------------------------------------------------------------------
 template <bool VEC2, int PL, int TX, int TY, int U>
 __global__ void __launch_bounds__(256) prep_kernel(Step s, const void* labels, int label_bytes,
-                                                   int nwb) {
+                                                   int nwb, int npub, P2P p) {
   static_assert(TX * TY == 256, "256 threads");
   pdl_trigger();            // first kernel of the step: nothing to wait for
   __shared__ float red[TY][2 * TX];
   const int tid = threadIdx.x;
-  if ((int)blockIdx.x < nwb) {
+  if ((int)blockIdx.x < npub) {
+    const unsigned cur = p2p_current_step(p);
+    float4* xs = reinterpret_cast<float4*>(p.x(p.rank, cur & 1));
+    int* ys = p.y(p.rank, cur & 1);
+    const size_t n4 = (size_t)p.b_local * p.D / 4;
+    for (size_t i = blockIdx.x * (size_t)256 + tid; i < n4; i += (size_t)npub * 256)
+      xs[i] = __ldg(reinterpret_cast<const float4*>(p.x_local) + i);
+    for (int i = blockIdx.x * 256 + tid; i < p.b_local; i += npub * 256)
+      ys[i] = p.y_bytes == 8 ? (int)reinterpret_cast<const long long*>(p.y_local)[i]
+                             : reinterpret_cast<const int*>(p.y_local)[i];
+    if (block_ticket(p.tickets + 0, (unsigned)npub) == (unsigned)npub - 1 && tid == 0)
+      p2p_publish(p, 0, cur);
+    return;
+  }
+  const int bid = (int)blockIdx.x - npub;
+  if (bid < nwb) {
     const int tx = tid % TX, ty = tid / TX;
-    const int j0 = (blockIdx.x * TX + tx) * 2;
+    const int j0 = (bid * TX + tx) * 2;
     float a0 = 0.f, a1 = 0.f;
     if (j0 < s.Cp) {
       const bool v0 = j0 < s.C, v1 = j0 + 1 < s.C;
@@ -45,7 +68,10 @@ __global__ void __launch_bounds__(256) prep_kernel(Step s, const void* labels, i
           if (d < s.D) {
             if (VEC2) {
               if (v1) {
-                const float2 v = __ldg(reinterpret_cast<const float2*>(w + (size_t)d * s.C));
+                // the fp32 master weights are read once per step: evict-first keeps the bf16
+                // copy written below (what the GEMM kernels read next) resident in L2 instead
+                const float2* wp = reinterpret_cast<const float2*>(w + (size_t)d * s.C);
+                const float2 v = s.l2_hints ? __ldcs(wp) : __ldg(wp);
                 x0[u] = v.x; x1[u] = v.y;
               } else if (v0) {
                 x0[u] = __ldg(w + (size_t)d * s.C);
@@ -82,25 +108,41 @@ __global__ void __launch_bounds__(256) prep_kernel(Step s, const void* labels, i
       float acc = 0.f;
 #pragma unroll
       for (int r = 0; r < TY; ++r) acc += red[r][t];
-      const int j = blockIdx.x * 2 * TX + t;
+      const int j = bid * 2 * TX + t;
       if (j < s.Cp) s.inv_c[j] = (j < s.C && acc > 0.f) ? rsqrtf(acc) : 0.f;
     }
   } else {
     const int tx = tid & 31;
-    const int row = (blockIdx.x - nwb) * 8 + (tid >> 5);
+    const int row = (bid - nwb) * 8 + (tid >> 5);
     if (row >= s.B) return;
     const float* x = s.X + (size_t)row * s.D;
+    float* xg = nullptr;
+    long long y;
+    if (npub > 0) {
+      // gathered batch: row `row` lives in the symmetric block of rank row / b_local
+      const unsigned cur = p2p_current_step(p);
+      const int src = row / p.b_local, lr = row - src * p.b_local;
+      if (tx == 0) p2p_wait(p, 0, src, cur);
+      __syncwarp();
+      x = p.x(src, cur & 1) + (size_t)lr * s.D;
+      xg = p.Xg + (size_t)row * s.D;             // fp32 copy for the r_i x_i term of dX
+      y = (long long)__ldcv(p.y(src, cur & 1) + lr);
+    } else {
+      y = label_bytes == 8 ? reinterpret_cast<const long long*>(labels)[row]
+                           : (long long)reinterpret_cast<const int*>(labels)[row];
+    }
     float acc = 0.f;
     for (int d = tx; d < s.D; d += 32) {
-      const float v = __ldg(x + d);
+      const float v = npub > 0 ? __ldcv(x + d) : __ldg(x + d);
+      if (npub > 0) xg[d] = v;
       acc = fmaf(v, v, acc);
       if (PL > 0) {
         __nv_bfloat16* dst = s.Xb + (size_t)row * PL * s.D + d;
         float r = v;
 #pragma unroll
-        for (int p = 0; p < PL; ++p) {
+        for (int p2 = 0; p2 < PL; ++p2) {
           const __nv_bfloat16 hv = __float2bfloat16_rn(r);
-          dst[(size_t)p * s.D] = hv;
+          dst[(size_t)p2 * s.D] = hv;
           r -= __bfloat162float(hv);
         }
       }
@@ -110,10 +152,9 @@ __global__ void __launch_bounds__(256) prep_kernel(Step s, const void* labels, i
       const float nn = sqrtf(acc);
       s.n[row] = nn;
       s.inv_n[row] = nn > 0.f ? 1.0f / nn : 0.f;
-      long long y = label_bytes == 8 ? reinterpret_cast<const long long*>(labels)[row]
-                                     : (long long)reinterpret_cast<const int*>(labels)[row];
-      // -1: owned by another shard; -2: outside [0, C_total) (reported by asm_check_labels;
-      // both mean "no target column here" to every kernel, so a bad label never faults)
+      // -1: owned by another shard; -2: outside [0, C_total) (reported by asm_check_labels, and
+      // the row's loss becomes NaN; both mean "no target column here" to the GEMM kernels, so a
+      // bad label never faults)
       const long long yl = y - s.class_offset;
       s.ylocal[row] = (y < 0 || y >= s.C_total) ? -2 : ((yl >= 0 && yl < s.C) ? (int)yl : -1);
       s.tgt_s[row] = 0.f;
@@ -123,24 +164,32 @@ __global__ void __launch_bounds__(256) prep_kernel(Step s, const void* labels, i
 }
 
 template <int TX, int TY, int U>
-static void launch_prep_t(const Step& s, const void* labels, int label_bytes, cudaStream_t st) {
+static void launch_prep_t(const Step& s, const void* labels, int label_bytes, cudaStream_t st, const P2P* p) {
   const int nwb = (s.Cp + 2 * TX - 1) / (2 * TX);
   const int nxb = (s.B + 7) / 8;
+  int npub = 0;
+  P2P pp{};
+  if (p != nullptr && p->world > 1) {
+    pp = *p;
+    npub = (int)(((size_t)p->b_local * p->D / 4 + 2047) / 2048);     // 8 float4 per thread
+    if (npub < 1) npub = 1;
+    if (npub > 32) npub = 32;
+  }
   const bool vec2 = (s.C % 2 == 0) && ((reinterpret_cast<uintptr_t>(s.W) & 7) == 0);
-  dim3 grd(nwb + nxb);
+  dim3 grd(npub + nwb + nxb);
   if (s.x3) {
-    if (vec2) prep_kernel<true, 3, TX, TY, U><<<grd, 256, 0, st>>>(s, labels, label_bytes, nwb);
-    else prep_kernel<false, 3, TX, TY, U><<<grd, 256, 0, st>>>(s, labels, label_bytes, nwb);
+    if (vec2) prep_kernel<true, 3, TX, TY, U><<<grd, 256, 0, st>>>(s, labels, label_bytes, nwb, npub, pp);
+    else prep_kernel<false, 3, TX, TY, U><<<grd, 256, 0, st>>>(s, labels, label_bytes, nwb, npub, pp);
   } else if (s.mode == 1) {
-    if (vec2) prep_kernel<true, 1, TX, TY, U><<<grd, 256, 0, st>>>(s, labels, label_bytes, nwb);
-    else prep_kernel<false, 1, TX, TY, U><<<grd, 256, 0, st>>>(s, labels, label_bytes, nwb);
+    if (vec2) prep_kernel<true, 1, TX, TY, U><<<grd, 256, 0, st>>>(s, labels, label_bytes, nwb, npub, pp);
+    else prep_kernel<false, 1, TX, TY, U><<<grd, 256, 0, st>>>(s, labels, label_bytes, nwb, npub, pp);
   } else {
-    if (vec2) prep_kernel<true, 0, TX, TY, U><<<grd, 256, 0, st>>>(s, labels, label_bytes, nwb);
-    else prep_kernel<false, 0, TX, TY, U><<<grd, 256, 0, st>>>(s, labels, label_bytes, nwb);
+    if (vec2) prep_kernel<true, 0, TX, TY, U><<<grd, 256, 0, st>>>(s, labels, label_bytes, nwb, npub, pp);
+    else prep_kernel<false, 0, TX, TY, U><<<grd, 256, 0, st>>>(s, labels, label_bytes, nwb, npub, pp);
   }
 }
 
-void launch_prep(const Step& s, const void* labels, int label_bytes, cudaStream_t st) {
+void launch_prep(const Step& s, const void* labels, int label_bytes, cudaStream_t st, const P2P* p) {
   // Block shape (column pairs x row groups) and loads in flight per thread.  Measured at
   // cfg 3 (263.9 MB): 32x8/U=4 51.7 us (5.1 TB/s), 16x16/U=8 51.7, 32x8/U=8 53.2,
   // 32x8/U=16 59.8, 32x8/U=32 94, 32x8/U=2 65, 128x2/U=16 73: occupancy beats unroll depth,
@@ -156,13 +205,13 @@ void launch_prep(const Step& s, const void* labels, int label_bytes, cudaStream_
     small_auto = (e && atoi(e) != 0) ? 1 : 0;
   }
   if (shape == 0 && small_auto && s.Cp <= 32768) {
-    launch_prep_t<16, 16, 8>(s, labels, label_bytes, st);
+    launch_prep_t<16, 16, 8>(s, labels, label_bytes, st, p);
     return;
   }
-  if (shape == 1) launch_prep_t<32, 8, 16>(s, labels, label_bytes, st);
-  else if (shape == 2) launch_prep_t<16, 16, 8>(s, labels, label_bytes, st);
-  else if (shape == 3) launch_prep_t<128, 2, 16>(s, labels, label_bytes, st);
-  else launch_prep_t<32, 8, 4>(s, labels, label_bytes, st);
+  if (shape == 1) launch_prep_t<32, 8, 16>(s, labels, label_bytes, st, p);
+  else if (shape == 2) launch_prep_t<16, 16, 8>(s, labels, label_bytes, st, p);
+  else if (shape == 3) launch_prep_t<128, 2, 16>(s, labels, label_bytes, st, p);
+  else launch_prep_t<32, 8, 4>(s, labels, label_bytes, st, p);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -187,7 +236,7 @@ __global__ void __launch_bounds__(256) combine_local_kernel(Step s) {
     ms_combine(m, z, m2, z2);
   }
   if (lane == 0) {
-    float* st = s.stats_local + (s.par_step ? (size_t)(*s.par_step & 1) * s.stats_par_stride : 0);
+    float* st = s.stats_local;
     st[row] = m;
     st[s.B + row] = z;
     st[2 * s.B + row] = s.ylocal[row] >= 0 ? s.tgt_f[row] : 0.f;
@@ -244,55 +293,19 @@ __global__ void __launch_bounds__(256) combine_kernel(Step s, const float* stats
       fy += __shfl_xor_sync(0xffffffffu, fy, o);
     }
     if (lane == 0) {
-      const bool owned = yl_row >= 0;
       if (FUSED) {
-        fy = owned ? tgt_f_row : 0.f;
+        fy = yl_row >= 0 ? tgt_f_row : 0.f;
         s.stats_local[row] = m;
         s.stats_local[s.B + row] = z;
         s.stats_local[2 * s.B + row] = fy;
       }
-      const float lse = m + logf(z);
-      s.lse[row] = lse;
-      s.negoff[row] = -lse * 1.4426950408889634f + log2f(s.invB);
-      s.rowloss[row] = lse - fy;
-      float gt = 0.f, r = 0.f;
-      if (owned) {
-        const float inv_n = inv_n_row;
-        float psi, dpsi;
-        const float t = fminf(1.f, fmaxf(-1.f, tgt_s_row * inv_n));
-        psi_eval(t, s.m, psi, dpsi);
-        const float gy = (expf(tgt_f_row - lse) - 1.0f) * s.invB;
-        const float lam = step_lambda(s.lambda, s.lambda_dev);
-        const float il = 1.0f / (1.0f + lam);
-        gt = gy * (lam + dpsi) * il;
-        r = gy * (psi - t * dpsi) * il * inv_n;
-      }
-      s.gtarget[row] = gt;
-      s.rcoef[row] = r;
+      row_epilogue(s, row, m, z, fy, yl_row, tgt_f_row, tgt_s_row, inv_n_row);
     }
   }
   // With gradients the backward kernels do not need the mean loss: its reduction is deferred
   // to an idle warp of the dX kernel so that the recompute kernel can start right away.
   if (s.defer_loss) return;
-  // last block done: fixed-order sum of the per-row losses
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) is_last = (atomicAdd(s.counter, 1u) == gridDim.x - 1);
-  __syncthreads();
-  if (!is_last) return;
-  __threadfence();
-  float acc = 0.f;
-  for (int i = threadIdx.x; i < s.B; i += 256) acc += __ldcg(s.rowloss + i);
-  red[threadIdx.x] = acc;
-  __syncthreads();
-  for (int o = 128; o > 0; o >>= 1) {
-    if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) {
-    if (s.loss) *s.loss = red[0] * s.invB;
-    *s.counter = 0u;
-  }
+  last_block_loss(s, red, &is_last);
 }
 
 void launch_combine_global(const Step& s, const float* stats_all, int n_shards, cudaStream_t st) {
@@ -307,47 +320,11 @@ void launch_combine_fused(const Step& s, cudaStream_t st) {
 // ---------------------------------------------------------------------------------------
 // dx_finish: dX = sum_z dx_part[z] + r_i * x_i   (float4 along D; D % 4 == 0)
 // ---------------------------------------------------------------------------------------
-// KS_T > 0: all KS_T partial loads are issued before the first add (one memory round trip);
-// KS_T == 0: generic loop in batches of four.  Summation order z = 0..KS-1 either way.
 template <int KS_T>
 __global__ void __launch_bounds__(256) dx_finish_kernel(Step s) {
   pdl_trigger();
   pdl_wait();
-  const size_t total4 = (size_t)s.B * s.D / 4;
-  const size_t stride4 = total4;
-  float* dxo = s.dX + (s.par_step ? (size_t)(*s.par_step & 1) * s.dx_par_stride : 0);
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total4;
-       i += (size_t)gridDim.x * blockDim.x) {
-    const int row = (int)((i * 4) / s.D);
-    const float4* p = reinterpret_cast<const float4*>(s.dx_part) + i;
-    const float r = s.rcoef[row];
-    const float4 x = __ldg(reinterpret_cast<const float4*>(s.X) + i);
-    float4 a = make_float4(r * x.x, r * x.y, r * x.z, r * x.w);
-    if (KS_T > 0) {
-      float4 v[KS_T > 0 ? KS_T : 1];
-#pragma unroll
-      for (int z = 0; z < KS_T; ++z) v[z] = __ldcg(p + (size_t)z * stride4);
-#pragma unroll
-      for (int z = 0; z < KS_T; ++z) { a.x += v[z].x; a.y += v[z].y; a.z += v[z].z; a.w += v[z].w; }
-    } else {
-      int z = 0;
-      for (; z + 4 <= s.KS; z += 4) {
-        const float4 v0 = __ldcg(p + (size_t)(z + 0) * stride4);
-        const float4 v1 = __ldcg(p + (size_t)(z + 1) * stride4);
-        const float4 v2 = __ldcg(p + (size_t)(z + 2) * stride4);
-        const float4 v3 = __ldcg(p + (size_t)(z + 3) * stride4);
-        a.x += v0.x; a.y += v0.y; a.z += v0.z; a.w += v0.w;
-        a.x += v1.x; a.y += v1.y; a.z += v1.z; a.w += v1.w;
-        a.x += v2.x; a.y += v2.y; a.z += v2.z; a.w += v2.w;
-        a.x += v3.x; a.y += v3.y; a.z += v3.z; a.w += v3.w;
-      }
-      for (; z < s.KS; ++z) {
-        const float4 v = __ldcg(p + (size_t)z * stride4);
-        a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
-      }
-    }
-    reinterpret_cast<float4*>(dxo)[i] = a;
-  }
+  dx_finish_rows<KS_T>(s, s.dX, blockIdx.x, gridDim.x);
 }
 
 void launch_dx_finish(const Step& s, cudaStream_t st) {
@@ -415,6 +392,30 @@ void launch_opt_stream(const Step& s, const float* dW, cudaStream_t st) {
     launch_pdl(opt_stream_kernel<1>, dim3((unsigned)blocks), dim3(256), 0, st, false, 1, dW, s.Wmut, s.opt_s0,
                s.opt_s1, n, s.opt);
   }
+}
+
+template <int TX, int TY, int U>
+static void preload_prep_t() {
+  cudaFuncAttributes a;
+  cudaFuncGetAttributes(&a, prep_kernel<true, 3, TX, TY, U>);
+  cudaFuncGetAttributes(&a, prep_kernel<false, 3, TX, TY, U>);
+  cudaFuncGetAttributes(&a, prep_kernel<true, 1, TX, TY, U>);
+  cudaFuncGetAttributes(&a, prep_kernel<false, 1, TX, TY, U>);
+  cudaFuncGetAttributes(&a, prep_kernel<true, 0, TX, TY, U>);
+  cudaFuncGetAttributes(&a, prep_kernel<false, 0, TX, TY, U>);
+}
+void prep_preload_kernels() {
+  preload_prep_t<16, 16, 8>();
+  preload_prep_t<32, 8, 16>();
+  preload_prep_t<128, 2, 16>();
+  preload_prep_t<32, 8, 4>();
+  cudaFuncAttributes a;
+  cudaFuncGetAttributes(&a, combine_local_kernel);
+  cudaFuncGetAttributes(&a, combine_kernel<true>);
+  cudaFuncGetAttributes(&a, combine_kernel<false>);
+  cudaFuncGetAttributes(&a, dx_finish_kernel<0>);
+  cudaFuncGetAttributes(&a, opt_stream_kernel<4>);
+  cudaFuncGetAttributes(&a, opt_stream_kernel<1>);
 }
 
 }  // namespace asmh

@@ -306,4 +306,12 @@ void launch_simt_dx(const Step& s, cudaStream_t st) {
   simt_kernel<K_DX><<<g3, 256, 0, st>>>(s, kper);
 }
 
+void simt_preload_kernels() {
+  cudaFuncAttributes a;
+  cudaFuncGetAttributes(&a, simt_kernel<K_FWD>);
+  cudaFuncGetAttributes(&a, simt_kernel<K_BWDG>);
+  cudaFuncGetAttributes(&a, simt_kernel<K_DW>);
+  cudaFuncGetAttributes(&a, simt_kernel<K_DX>);
+}
+
 }  // namespace asmh

@@ -97,6 +97,21 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* s
       "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
       : "memory");
 }
+// same, with an L2 cache-policy operand (e.g. kEvictFirst for data nothing reads again soon)
+__device__ __forceinline__ void tma_store_2d_hint(const CUtensorMap* m, const void* smem_src,
+                                                  int32_t c0, int32_t c1, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;" ::"l"(
+          reinterpret_cast<uint64_t>(m)),
+      "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "l"(policy)
+      : "memory");
+}
+// L2 cache policy for the .L2::cache_hint operand of bulk copies
+__device__ __forceinline__ uint64_t policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
 __device__ __forceinline__ void bulk_commit() {
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }

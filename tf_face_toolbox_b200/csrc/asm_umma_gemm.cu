@@ -20,9 +20,19 @@
 // lanes of a warp write 32 consecutive classes of G'' / dW).  The bf16 copy of W keeps the
 // reference's [D, C] orientation (no transpose anywhere), every operand is read by TMA with
 // 128-byte swizzle, and nothing but [B]-sized statistics leaves the forward kernel.
+#include <type_traits>
+
 #include "asm_common.cuh"
 #include "asm_kernels.cuh"
 #include "asm_umma.cuh"
+
+// Bring-up knobs (ASM_UMMA_DEBUG bits: skip the epilogue math, experimental kernel variants)
+// exist only in a -DASM_BRINGUP build; the default library cannot be told to skip work.
+#ifdef ASM_BRINGUP
+#define ASM_DBG(flags, bit) ((flags) & (bit))
+#else
+#define ASM_DBG(flags, bit) 0
+#endif
 
 namespace asmh {
 
@@ -41,6 +51,7 @@ constexpr int STG_HALF = 32 * 128 * 2;         // G'' staging per column half: 3
 constexpr int AUX_STG = 2 * STG_HALF;          // 16 KB
 constexpr int WB_BUF = 32 * 128 * 2;           // DW: one [32 d x 128 classes] bf16 weight chunk
 constexpr int AUX_WB = 2 * 2 * WB_BUF;         // 2 column halves x 2 buffers = 32 KB
+constexpr int DSTG = 32 * 128 * 4;             // DW: one [32 d x 128 classes] fp32 staging block of dW (16 KB)
 // the region after the barriers holds vec + stg (FWD / BWDG) or the weight-chunk ring (DW)
 constexpr int AUX_REGION = (AUX_VEC + AUX_STG) > AUX_WB ? (AUX_VEC + AUX_STG) : AUX_WB;
 constexpr float LOG2E = 1.4426950408889634f;
@@ -63,11 +74,13 @@ enum { U_FWD = 0, U_BWDG = 1, U_DW = 2, U_DX = 3, U_FWDR = 4, U_DWOPT = 5, U_DWF
 template <int KIND, int CG = 1, int BNT = BN_FULL> struct Geo {
   static constexpr bool RES = (KIND == U_FWDR);
   static constexpr int KB = (RES && CG == 1) ? 32 : BK;    // K elements per pipeline stage
-  // the dW kernel of a CTA pair trades its 6th operand stage for a 4-deep weight-chunk ring
-  static constexpr int NWB = (KIND == U_DW && CG == 2) ? 4 : 2;  // weight-chunk buffers per column half
+  static constexpr int NWB = 2;                            // weight-chunk buffers per column half
+  // the dW kernel of a CTA pair stages its output in shared memory and leaves through TMA
+  // stores (two [32 d x 128 classes] fp32 buffers per column half), paid for with two operand stages
+  static constexpr bool DW_TMA = (KIND == U_DW && CG == 2);
   // the BWDG kernel of a CTA pair trades its 6th operand stage for double-buffered G'' staging
   static constexpr int NSB = (KIND == U_BWDG && CG == 2) ? 2 : 1;   // G'' staging buffers per column half
-  static constexpr int NST = RES ? 5 : (CG == 2 ? ((KIND == U_DW || KIND == U_BWDG) ? 5 : 6) : STAGES);   // pipeline depth
+  static constexpr int NST = RES ? 5 : (CG == 2 ? (DW_TMA ? 4 : (KIND == U_BWDG ? 5 : 6)) : STAGES);   // pipeline depth
   static constexpr int A_ST = RES ? 0 : BM * KB * 2;       // A bytes per stage
   static constexpr int B_ST = BNT * KB * 2 / CG;           // B bytes per stage (per CTA)
   static constexpr int ST_B = A_ST + B_ST;
@@ -75,7 +88,7 @@ template <int KIND, int CG = 1, int BNT = BN_FULL> struct Geo {
   static constexpr int CH_B = 64 * KB * 2;                 // one 64-wide MN-major chunk
   static constexpr int PIPE_B = RES_B + NST * ST_B;
   static constexpr int AUX_R = RES ? AUX_VEC
-                               : (KIND == U_DW ? 2 * NWB * WB_BUF
+                               : (KIND == U_DW ? 2 * NWB * WB_BUF + (DW_TMA ? 4 * DSTG : 0)
                                                : (NSB == 2 ? AUX_VEC + 2 * AUX_STG : AUX_REGION));
   static constexpr int SMEM = PIPE_B + AUX_BARS + AUX_R + 1024;
   static_assert(SMEM <= 232448, "exceeds the 227 KB shared memory of an sm_100 CTA");
@@ -114,7 +127,8 @@ __device__ __noinline__ float fwd_target(float* tgt_s, float* tgt_f, const float
 template <int KIND, int CG = 1, int BNT = BN_FULL>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-            const __grid_constant__ CUtensorMap mapC, Step s, UmmaArgs g) {
+            const __grid_constant__ CUtensorMap mapC, const __grid_constant__ CUtensorMap mapD,
+            const __grid_constant__ CUtensorMap mapE, Step s, UmmaArgs g) {
   using G_ = Geo<KIND, CG, BNT>;
   constexpr int BN = BNT;                 // tile width of this instantiation (shadows the default)
   constexpr int HC = BN / 2;              // accumulator columns per epilogue half
@@ -153,6 +167,7 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
   uint8_t* stg = smem + PIPE_B + AUX_BARS + AUX_VEC;                  // BWDG: [2 halves][NSB][STG_HALF]
   constexpr int NSB = G_::NSB;
   uint8_t* wbuf = smem + PIPE_B + AUX_BARS;                           // DW: [2][2][WB_BUF]
+  uint8_t* dstg = wbuf + 2 * NWB * WB_BUF;                            // DW (pairs): [2 halves][2][DSTG]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -160,6 +175,7 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
     ptx::prefetch_tmap(&mapA);
     ptx::prefetch_tmap(&mapB);
     if (IS_BWDG || KIND == U_DW) ptx::prefetch_tmap(&mapC);
+    if (G_::DW_TMA) { ptx::prefetch_tmap(&mapD); ptx::prefetch_tmap(&mapE); }
   }
   if (warp == 1 && ptx::elect_one()) {
     for (int i = 0; i < NST; ++i) {
@@ -196,6 +212,22 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
     const int t = u - z * tiles_mn;
     if (N_FAST) { m_idx = t / g.nt; n_idx = t - m_idx * g.nt; }
     else        { n_idx = t / g.mt; m_idx = t - n_idx * g.mt; }
+    // class tiles in descending order: consecutive kernels of a step sweep the classes in
+    // opposite directions, so each starts on what its predecessor left in L2
+    if (g.rev) { if (N_FAST) m_idx = g.mt - 1 - m_idx; else n_idx = g.nt - 1 - n_idx; }
+  };
+  // K blocks of split z.  Contiguous ranges [z kb_per, (z+1) kb_per) by default; with
+  // g.kstride (dX: K = classes) split z takes blocks z, z + ks, z + 2 ks, ... so that ALL CTAs
+  // sweep the class range together (descending when g.rev) -- the sweep starts on the classes
+  // the preceding kernel touched last, which are still in L2.
+  auto kcount = [&](int z) {
+    if (g.kstride) return (g.kb_total - z + g.ks - 1) / g.ks;
+    const int kb0 = z * g.kb_per;
+    return min(g.kb_total, kb0 + g.kb_per) - kb0;
+  };
+  auto kblock = [&](int z, int i) {
+    if (g.kstride) return g.rev ? g.kb_total - 1 - (z + i * g.ks) : z + i * g.ks;
+    return z * g.kb_per + i;
   };
 
   if (warp == 0) {
@@ -221,8 +253,9 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
         int z, m_idx, n_idx;
         decode(u, z, m_idx, n_idx);
         const int m0 = (m_idx * CG + crank) * BM, n0 = n_idx * BN;
-        const int kb0 = z * g.kb_per, kb1 = min(g.kb_total, kb0 + g.kb_per);
-        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+        const int nk = kcount(z);
+        for (int ki = 0; ki < nk; ++ki, ++it) {
+          const int kb = kblock(z, ki);
           const int st = it % NST;
           const uint32_t ph = (it / NST) & 1;
           ptx::mbar_wait(&empty[st], ph ^ 1);
@@ -293,12 +326,13 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
       if (RES && pair_id < total) ptx::mbar_wait(&wfull[0], 0);   // resident Xb landed
       for (int u = pair_id; u < total; u += npairs, ++lt) {
         const int z = u / tiles_mn;
-        const int kb0 = z * g.kb_per, kb1 = min(g.kb_total, kb0 + g.kb_per);
+        const int nk = kcount(z);
         const uint32_t a = lt & 1, aph = (lt >> 1) & 1;
         ptx::mbar_wait(&tempty[a], aph ^ 1);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + a * BN_FULL;
-        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+        for (int ki = 0; ki < nk; ++ki, ++it) {
+          const int kb = RES ? kblock(z, ki) : 0;     // only the resident-A variant addresses by kb
           const int st = it % NST;
           const uint32_t ph = (it / NST) & 1;
           ptx::mbar_wait(&full[st], ph);
@@ -312,11 +346,11 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
             if (CG == 2)
               ptx::umma_bf16_cg2(d_tmem, ptx::smem_desc(hiA, aA + kk * stepA),
                                  ptx::smem_desc(hiB, aB + kk * stepB), idesc,
-                                 (kb > kb0 || kk > 0) ? 1u : 0u);
+                                 (ki > 0 || kk > 0) ? 1u : 0u);
             else
               ptx::umma_bf16(d_tmem, ptx::smem_desc(hiA, aA + kk * stepA),
                              ptx::smem_desc(hiB, aB + kk * stepB), idesc,
-                             (kb > kb0 || kk > 0) ? 1u : 0u);
+                             (ki > 0 || kk > 0) ? 1u : 0u);
           }
           // frees the smem slot (in both CTAs of a pair) when these MMAs retire
           if (CG == 2) ptx::umma_commit_cg2(&empty[st]); else ptx::umma_commit(&empty[st]);
@@ -330,7 +364,7 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
     // Streams the bf16 weight block of each tile ([256 d x 128 classes], needed by the
     // normalisation-Jacobian correction in the epilogue) through a 2-deep ring per column
     // half, so the epilogue never waits on a global load.
-    if (KIND == U_DW && !(g.debug_flags & 1) && ptx::elect_one()) {
+    if (KIND == U_DW && !ASM_DBG(g.debug_flags, 1) && ptx::elect_one()) {
       uint32_t cc = 0;
       for (int u = pair_id; u < total; u += npairs) {
         int z, m_idx, n_idx;
@@ -431,7 +465,7 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
       float* v1 = vec1 + a * BN_FULL;
       float* v2 = vec2 + a * BN_FULL;
       uint32_t r0[32], r1[32];
-      if (g.debug_flags & 1) {                // bring-up knob: mainloop only, no epilogue math
+      if (ASM_DBG(g.debug_flags, 1)) {        // bring-up knob: mainloop only, no epilogue math
         ptx::mbar_wait(&tfull[a], aph);
         ptx::tc_fence_after();
         release_acc(a);
@@ -548,26 +582,40 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
         ptx::mbar_wait(&tfull[a], aph);
         ptx::tc_fence_after();
         float q0 = 0.f, q1 = 0.f;                             // sum_i G'_ij * acc_ij  (x ic later)
+        const int jw0 = m0 + q4 * 32;                         // first class of this warp
         auto process = [&](const uint32_t (&r)[32], int c) {
           const int cb = col0 + c * 32;
           const int ib = n0 + cb;                             // first batch row of the chunk
           float gq[32];
+          // Target column G'_{i,y}: at most one element per batch row, and only when that row's
+          // label is one of this warp's 32 classes.  A ballot makes the test warp-uniform, so the
+          // hot variant of the loop carries no per-element compare at all; the patching variant
+          // (same arithmetic as before, the target replaced BEFORE it enters q_j) runs rarely.
+          const int ylane = __float_as_int(v1[cb + lane]);    // local class index of row ib + lane
+          const bool hit = __ballot_sync(0xffffffffu, static_cast<unsigned>(ylane - jw0) < 32u) != 0u;
+          auto body = [&](auto patch_tag) {
+            constexpr bool PATCH = decltype(patch_tag)::value;
 #pragma unroll
-          for (int b4 = 0; b4 < 8; ++b4) {
-            const float4 no = *reinterpret_cast<const float4*>(v0 + cb + b4 * 4);
-            const int4 yy = *reinterpret_cast<const int4*>(v1 + cb + b4 * 4);
-            const float nof[4] = {no.x, no.y, no.z, no.w};
-            const int yv[4] = {yy.x, yy.y, yy.z, yy.w};
+            for (int b4 = 0; b4 < 8; ++b4) {
+              const float4 no = *reinterpret_cast<const float4*>(v0 + cb + b4 * 4);
+              const float nof[4] = {no.x, no.y, no.z, no.w};
+              int yv[4] = {0, 0, 0, 0};
+              if (PATCH) {
+                const int4 yy = *reinterpret_cast<const int4*>(v1 + cb + b4 * 4);
+                yv[0] = yy.x; yv[1] = yy.y; yv[2] = yy.z; yv[3] = yy.w;
+              }
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int b = b4 * 4 + e;
-              const float acc = __uint_as_float(r[b]);
-              float gp = fast_ex2(fmaf(acc, icl, nof[e]));    // softmax prob / B
-              if (yv[e] == j) gp = v2[cb + b];                // target column: G'_{i,y}
-              if (e & 1) q1 = fmaf(gp, acc, q1); else q0 = fmaf(gp, acc, q0);
-              gq[b] = gp * ic;
+              for (int e = 0; e < 4; ++e) {
+                const int b = b4 * 4 + e;
+                const float acc = __uint_as_float(r[b]);
+                float gp = fast_ex2(fmaf(acc, icl, nof[e]));    // softmax prob / B
+                if (PATCH && yv[e] == j) gp = v2[cb + b];       // target column: G'_{i,y}
+                if (e & 1) q1 = fmaf(gp, acc, q1); else q0 = fmaf(gp, acc, q0);
+                gq[b] = gp * ic;
+              }
             }
-          }
+          };
+          if (hit) body(std::true_type{}); else body(std::false_type{});
           // x3: G'' leaves as two bf16 planes (value, then the rounding residual), side by side
           const int npl = s.x3 ? 2 : 1;
 #pragma unroll 1
@@ -595,12 +643,26 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
       } else if (KIND == U_DW) {
         // ---- thread = class j, columns = d.  dW[d][j] = acc - Wb[d][j] * q_j / c_j^2
         // The q_j partials and 1/c_j were fetched one tile ahead; the bf16 weight chunks
-        // arrive through the TMA ring filled by warp 3.
+        // arrive through the TMA ring filled by warp 3.  CTA pairs stage each
+        // [32 d x 128 classes] fp32 block in shared memory (even d rows first, then the odd
+        // ones) and one thread writes it with two TMA stores on the [D/2, 2C] view of the
+        // caller's dW (row pitch 8C bytes is a multiple of 16 for even C: row d -> view row
+        // d/2, column (d & 1) C + j); columns >= C are clipped by the tensor extent.
         const int j = m0 + lane_row;
         const bool jv = j < s.C;
         const float coef = -(((pre0 + pre1) + (pre3 + pre4)) + pre5) * pre2 * pre2;
         prefetch_tile(u + npairs);
         const int d_first = n0 + col0;
+        const bool dw_tma = G_::DW_TMA && g.dw_tma;
+        const int dw_sh = g.dw_shift;                         // 0, or 2 when C % 4 == 2
+        const int dw_op = 128 - 2 * dw_sh;                    // classes per odd-row box
+        const bool dw_edge = dw_sh != 0 && (lane_row < dw_sh || lane_row >= 128 - dw_sh);
+        uint8_t* dstg_half = dstg + half * 2 * DSTG;
+        const bool leader = (threadIdx.x == 128 + half * 128);
+        // nothing reads dW inside the step: mark its lines evict-first so that they do not push
+        // the operands the next kernels read (G'', the bf16 weights) out of L2
+        uint64_t store_policy = 0;
+        if (dw_tma && leader && g.store_evict_first) store_policy = ptx::policy_evict_first();
         ptx::mbar_wait(&tfull[a], aph);
         ptx::tc_fence_after();
         auto process = [&](const uint32_t (&r)[32], int c) {
@@ -616,7 +678,42 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
                         __uint_as_float(r[b]));
           ptx::mbar_arrive(&wempty[half * NWB + buf]);       // chunk consumed (values in o[])
           const int db = d_first + c * 32;                    // first d of the chunk
-          if (jv && db < s.D && !(g.debug_flags & 2)) {       // D % 32 == 0 in bf16 mode
+          if (dw_tma) {
+            // before the barrier of chunk c the leader confirms that the stores of chunk c-1
+            // have drained their buffer -- the buffer chunk c+1 writes after that barrier
+            if (leader) ptx::bulk_wait_read0();
+            float* sbe = reinterpret_cast<float*>(dstg_half + (c & 1) * DSTG) + lane_row;
+            float* sbo = reinterpret_cast<float*>(dstg_half + (c & 1) * DSTG + DSTG / 2) + (lane_row - dw_sh);
+#pragma unroll
+            for (int b = 0; b < 32; b += 2) sbe[(b >> 1) * 128] = o[b];
+            if (!dw_edge) {
+#pragma unroll
+              for (int b = 1; b < 32; b += 2) sbo[(b >> 1) * dw_op] = o[b];
+            } else if (jv && db < s.D) {
+              // odd rows start 8 bytes off a 16-byte boundary when C % 4 == 2 and a TMA store
+              // must start on one: their box is shifted by two classes, and the two classes on
+              // either end of the CTA's 128 are written directly by the threads that own them
+              float* dst = s.dW + (size_t)(db + 1) * s.C + j;
+#pragma unroll
+              for (int b = 1; b < 32; b += 2) {
+                *dst = o[b];
+                dst += 2 * (size_t)s.C;
+              }
+            }
+            ptx::fence_proxy_async();                         // generic writes -> async proxy
+            named_bar_sync(2 + half, 128);
+            if (leader && db < s.D) {                         // D % 32 == 0 in bf16 mode
+              const uint8_t* src = dstg_half + (c & 1) * DSTG;
+              if (g.store_evict_first) {
+                ptx::tma_store_2d_hint(&mapD, src, m0, db >> 1, store_policy);                            // even d
+                ptx::tma_store_2d_hint(&mapE, src + DSTG / 2, s.C + m0 + dw_sh, db >> 1, store_policy);   // odd d
+              } else {
+                ptx::tma_store_2d(&mapD, src, m0, db >> 1);
+                ptx::tma_store_2d(&mapE, src + DSTG / 2, s.C + m0 + dw_sh, db >> 1);
+              }
+              ptx::bulk_commit();
+            }
+          } else if (jv && db < s.D) {
             float* dst = s.dW + (size_t)db * s.C + j;
 #pragma unroll
             for (int b = 0; b < 32; ++b) {
@@ -664,7 +761,7 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
         // 128-byte line) before working on the current one: the loads that follow hit L2.
         const int ht = et & 127;
         auto prefetch_chunk = [&](int pm0, int pdb) {
-          if (g.debug_flags & 16) return;                      // A/B knob: no prefetch
+          if (ASM_DBG(g.debug_flags, 16)) return;              // A/B knob: no prefetch
           // [32 d x 128 classes] fp32 per array: 4 lines per row (+1 when the row is not
           // line-aligned, covered by the first 32 threads)
           const int row = ht >> 2;
@@ -742,7 +839,7 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
       s.part[(size_t)fwd_row * s.NT + (pair_id / g.mt) * 2 + half] = make_float2(run_m, run_z);
   }
 
-  if (IS_BWDG && (threadIdx.x == 128 || threadIdx.x == 256)) ptx::bulk_wait0();
+  if ((IS_BWDG || G_::DW_TMA) && (threadIdx.x == 128 || threadIdx.x == 256)) ptx::bulk_wait0();
   ptx::tc_fence_before();
   __syncthreads();
   if (CG == 2) ptx::cluster_sync_all();       // the peer may still be read / signalled by the leader
@@ -774,14 +871,15 @@ EncodeTiledFn get_encode_fn() {
 
 // bf16 row-major [outer, inner] tensor with `pitch` elements per row; box = {box_inner, box_outer}
 bool encode_map(CUtensorMap* m, const void* base, uint64_t inner, uint64_t outer, uint64_t pitch,
-                uint32_t box_inner, uint32_t box_outer, bool swizzle128 = true) {
+                uint32_t box_inner, uint32_t box_outer, bool swizzle128 = true, bool f32 = false) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return false;
   cuuint64_t dims[2] = {inner, outer};
-  cuuint64_t strides[1] = {pitch * 2};
+  cuuint64_t strides[1] = {pitch * (f32 ? 4 : 2)};
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
-  return fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box,
+  return fn(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+            const_cast<void*>(base), dims, strides, box,
             estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
             swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
@@ -847,6 +945,21 @@ bool umma_build_maps(UmmaMaps* m, const Step& s) {
   return ok;
 }
 
+void umma_build_dw_maps(UmmaMaps* m, const Step& s) {
+  if (m->dw_ptr == s.dW && m->dw_ptr != nullptr) return;
+  m->dw_ptr = s.dW;
+  m->dw_ok = 0;
+  // [D/2, 2C] view: needs an even C (pitch 8C bytes % 16 == 0), an even D and a 16-byte base
+  if (s.dW == nullptr || (s.C & 1) || (s.D & 1) || (reinterpret_cast<uintptr_t>(s.dW) & 15)) return;
+  const uint64_t C = (uint64_t)s.C, rows = (uint64_t)s.D / 2;
+  // a TMA store must start on a 16-byte boundary: odd rows begin 4C bytes into a view row, so
+  // for C % 4 == 2 their box starts two classes later and is four classes narrower
+  const uint32_t odd_box = (s.C & 3) ? 124 : 128;
+  bool ok = encode_map(&m->dw_even, s.dW, C, rows, 2 * C, 128, 16, false, true);
+  ok &= encode_map(&m->dw_odd, s.dW, 2 * C, rows, 2 * C, odd_box, 16, false, true);
+  m->dw_ok = ok ? 1 : 0;
+}
+
 // x3 segment tables.  A contraction of two fp32 operands split as a = a0 + a1 + a2 (bf16
 // planes, |a_p| <= 2^-8p |a|) keeps the plane pairs with p + q <= 2: what is dropped is below
 // 2^-24 relative, the fp32 rounding level.  G'' carries two planes (its own error budget is the
@@ -902,12 +1015,13 @@ cudaError_t set_smem() {
 // launch with `units` work units (CTAs, or CTA pairs as clusters of 2)
 template <int KIND, int CG, int BNT = BN_FULL>
 void launch_k(int units, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c,
-              const Step& s, const UmmaArgs& g, cudaStream_t st) {
+              const Step& s, const UmmaArgs& g, cudaStream_t st, const CUtensorMap* d = nullptr,
+              const CUtensorMap* e = nullptr) {
   if (units <= 0) return;
   // DW follows an event record (the dX fork), everything else follows a kernel directly
   const bool pdl = s.pdl != 0 && KIND != U_DW && KIND != U_DWOPT && KIND != U_DWF;
   launch_pdl(umma_kernel<KIND, CG, BNT>, dim3(units * CG), dim3(NUM_THREADS), Geo<KIND, CG, BNT>::SMEM, st,
-             pdl, CG, a, b, c, s, g);
+             pdl, CG, a, b, c, d ? *d : c, e ? *e : c, s, g);
 }
 }  // namespace
 
@@ -915,11 +1029,13 @@ cudaError_t umma_configure() {
   cudaError_t e;
   if ((e = set_smem<U_FWD, 1>()) != cudaSuccess) return e;
   if ((e = set_smem<U_FWD, 2>()) != cudaSuccess) return e;
+#ifdef ASM_BRINGUP
   if ((e = set_smem<U_FWDR, 1>()) != cudaSuccess) return e;
   if ((e = set_smem<U_FWDR, 2>()) != cudaSuccess) return e;
+  if ((e = set_smem<U_BWDG1, 2>()) != cudaSuccess) return e;
+#endif
   if ((e = set_smem<U_BWDG, 1>()) != cudaSuccess) return e;
   if ((e = set_smem<U_BWDG, 2>()) != cudaSuccess) return e;
-  if ((e = set_smem<U_BWDG1, 2>()) != cudaSuccess) return e;
   if ((e = set_smem<U_DW, 1>()) != cudaSuccess) return e;
   if ((e = set_smem<U_DW, 2>()) != cudaSuccess) return e;
   if ((e = set_smem<U_DWOPT, 1>()) != cudaSuccess) return e;
@@ -949,6 +1065,7 @@ void launch_umma_forward(const Step& s, const UmmaMaps& m, const UmmaTuning& tu,
     launch_k<U_FWD, 2, 128>(units, m.xb_k, m.wb_mn, m.wb_mn, s, g, st);
     return;
   }
+#ifdef ASM_BRINGUP
   if (s.D <= 512 && (tu.debug_flags & 4) && cg == 2 && !s.x3) {
     // opt-in: Xb row tiles resident in both CTAs of a pair, only the weight halves stream
     g.kb_total = (s.D + BK - 1) / BK;
@@ -964,6 +1081,7 @@ void launch_umma_forward(const Step& s, const UmmaMaps& m, const UmmaTuning& tu,
     launch_k<U_FWDR, 1>(units, m.xb_k, m.wb_mn32, m.wb_mn32, s, g, st);
     return;
   }
+#endif
   set_segments(g, s.x3 != 0, (s.D + BK - 1) / BK, kSegHi, kSegLo, x3_segments(), s.D, s.Cp);
   if (cg == 2) launch_k<U_FWD, 2>(units, m.xb_k, m.wb_mn, m.wb_mn, s, g, st);
   else launch_k<U_FWD, 1>(units, m.xb_k, m.wb_mn, m.wb_mn, s, g, st);
@@ -978,9 +1096,12 @@ void launch_umma_bwdg(const Step& s, const UmmaMaps& m, const UmmaTuning& tu, in
   g.nt = (s.B + bn - 1) / bn;
   // A = weights, B = embeddings: the same plane pairs with the roles swapped
   set_segments(g, s.x3 != 0, (s.D + BK - 1) / BK, kSegLo, kSegHi, x3_segments(), s.Cp, s.D);
+  g.rev = tu.l2_order ? 1 : 0;  // the forward kernel swept the classes upwards: start where it stopped
   const int units = min(g.mt * g.nt, num_sms / cg);
   if (bn == 128) launch_k<U_BWDG, 2, 128>(units, m.wb_mn, m.xb_mn, m.g_st, s, g, st);   // X box: 64 rows per CTA
+#ifdef ASM_BRINGUP
   else if (cg == 2 && (tu.debug_flags & 8)) launch_k<U_BWDG1, 2>(units, m.wb_mn, m.xb_k, m.g_st, s, g, st);
+#endif
   else if (cg == 2) launch_k<U_BWDG, 2>(units, m.wb_mn, m.xb_k, m.g_st, s, g, st);
   else launch_k<U_BWDG, 1>(units, m.wb_mn, m.xb_k256, m.g_st, s, g, st);
 }
@@ -995,10 +1116,14 @@ void launch_umma_dw(const Step& s, const UmmaMaps& m, const UmmaTuning& tu, int 
   set_segments(g, s.x3 != 0, (s.B + BK - 1) / BK, kSegG, kSegO, x3_segments() < 5 ? x3_segments() : 5,
                s.Cp, s.D);
   const int units = min(g.mt * g.nt, num_sms / cg);
+  // upwards again (BWDG went down): the first class tiles are the ones BWDG wrote last
+  g.dw_tma = (tu.dw_tma && cg == 2 && s.opt.kind == 0 && !s.x3 && m.dw_ok && m.dw_ptr == s.dW) ? 1 : 0;
+  g.dw_shift = (s.C & 3) ? 2 : 0;
+  g.store_evict_first = (tu.l2_hints & 2) ? 1 : 0;
   if (bn == 128) {
     if (s.opt.kind != 0) launch_k<U_DWOPT, 2, 128>(units, m.g_mn, m.xb_mn, m.wb_box, s, g, st);
     else if (s.x3) launch_k<U_DWF, 2, 128>(units, m.g_mn, m.xb_mn, m.wb_box, s, g, st);
-    else launch_k<U_DW, 2, 128>(units, m.g_mn, m.xb_mn, m.wb_box, s, g, st);
+    else launch_k<U_DW, 2, 128>(units, m.g_mn, m.xb_mn, m.wb_box, s, g, st, &m.dw_even, &m.dw_odd);
     return;
   }
   if (s.opt.kind == 0 && s.x3) {
@@ -1010,7 +1135,7 @@ void launch_umma_dw(const Step& s, const UmmaMaps& m, const UmmaTuning& tu, int 
     if (cg == 2) launch_k<U_DWOPT, 2>(units, m.g_mn, m.xb_mn, m.wb_box, s, g, st);
     else launch_k<U_DWOPT, 1>(units, m.g_mn, m.xb_mn, m.wb_box, s, g, st);
   } else {
-    if (cg == 2) launch_k<U_DW, 2>(units, m.g_mn, m.xb_mn, m.wb_box, s, g, st);
+    if (cg == 2) launch_k<U_DW, 2>(units, m.g_mn, m.xb_mn, m.wb_box, s, g, st, &m.dw_even, &m.dw_odd);
     else launch_k<U_DW, 1>(units, m.g_mn, m.xb_mn, m.wb_box, s, g, st);
   }
 }
@@ -1025,6 +1150,10 @@ void launch_umma_dx(const Step& s, const UmmaMaps& m, const UmmaTuning& tu, int 
                s.Cp, s.Cp);
   g.ks = s.KS;
   g.kb_per = (g.kb_total + g.ks - 1) / g.ks;
+  if (tu.l2_order && !s.x3) {   // all splits sweep the classes together, downwards (DW went up)
+    g.kstride = 1;
+    g.rev = 1;
+  }
   const int units = min(g.mt * g.nt * g.ks, num_sms / cg);
   if (cg == 2) launch_k<U_DX, 2>(units, m.g_k, m.wb_k128, m.wb_k128, s, g, st);
   else launch_k<U_DX, 1>(units, m.g_k, m.wb_k, m.wb_k, s, g, st);
