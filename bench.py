@@ -2,14 +2,19 @@
 """Benchmark of the A-softmax head hot path (BASELINE.json metric).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                    [--workload cfg3|cfg1|cfg2_head|cfg4|cfg5_head] [--mode bf16|fp32]
+                    [--workload cfg3|cfg1|cfg2_head|cfg4|cfg5_head|cfg5] [--mode bf16|fp32]
 
 One "step" = one forward+backward pass of the head over one batch of synthetic input
 (everything behind asm_forward_backward: norms, contractions, epilogues; excluding the
 optimizer).  At N=1 the workload is BASELINE config 3 (C=85,742, D=512, batch 512, bf16), the
 configuration the metric is quoted on.  For N>1 (launched by torchrun, one rank per GPU) the
-same global batch is class-sharded over the ranks (strong scaling): all-gather X, one
-statistics all-gather, reduce-scatter dX -- no collective on dW.
+same global batch is class-sharded over the ranks (strong scaling): the embeddings gather, the
+statistics exchange and the dX reduce-scatter ride inside the head's own kernels over NVLink
+peer memory (transport "nvlink") or go through three NCCL collectives (transport "nccl") -- no
+collective on dW either way.
+
+Every launch path is run ONCE on the bench inputs and compared with the float64 oracle before
+anything is timed (`parity` in the JSON line); a failed gate exits non-zero without a number.
 
 Prints ONE JSON line on rank 0 (see the keys in main()).  `--impl reference` times the CPU
 stand-in for the reference's TensorFlow path (oracle/tf_graph_port.py; the TF code itself
@@ -34,6 +39,8 @@ METRIC = "A-softmax head fwd+bwd samples/sec at C=85,742 D=512, 1/2/4/8 B200"
 UNIT = "samples/s"
 M_MARGIN = 4
 LAMBDA = 5.0      # lambda_min of the SphereFace schedule (timing uses lambda=5)
+LOSS_TOL = {"fp32": 1e-5, "bf16": 2e-3}      # BASELINE.json north_star
+COS_MIN = 0.9999
 
 
 def load_peaks():
@@ -149,12 +156,309 @@ def run_reference(args, cfg):
 
 
 def workload_config(args, cfg, world):
-    return {"workload": f"{args.workload}: A-softmax head fwd+bwd, C={cfg['C']} D={cfg['D']} batch={cfg['B']} "
+    extra = " + center loss (loss.py:29-45)" if cfg.get("center") else ""
+    return {"workload": f"{args.workload}: A-softmax head fwd+bwd{extra}, C={cfg['C']} D={cfg['D']} batch={cfg['B']} "
                         f"m={M_MARGIN} lambda={LAMBDA} {args.mode}",
             "global_batch": cfg["B"], "num_classes": cfg["C"], "embedding_dim": cfg["D"],
             "parallelism": f"class-sharded x{world}" if world > 1 else "single shard",
             "l2": "inputs larger than L2 (W fp32 %.1f MB + bf16 operand copies; no explicit flush)" % (cfg["C"] * cfg["D"] * 4 / 1e6)
                   if cfg["C"] * cfg["D"] * 4 > 126e6 else "L2 flushed between timed iterations (256 MB write)"}
+
+
+def _cos(a, b):
+    import numpy as np
+    a = np.asarray(a, dtype=np.float64).ravel()
+    b = np.asarray(b, dtype=np.float64).ravel()
+    return float(a @ b / max(np.sqrt((a @ a) * (b @ b)), 1e-300))
+
+
+# ----------------------------------------------------------------------------------------
+# one workload on this process group: parity gate, then the timed loops
+# ----------------------------------------------------------------------------------------
+class Workload:
+    def __init__(self, args, cfg, mode, rank, world, dev, center=False):
+        import torch
+        import torch.distributed as dist
+        from tf_face_toolbox_b200 import ShardedASoftmaxHead
+        from tf_face_toolbox_b200.synthetic import make_inputs
+        self.args, self.cfg, self.mode, self.rank, self.world, self.dev = args, cfg, mode, rank, world, dev
+        self.torch, self.dist = torch, dist
+        B, D, Cn = cfg["B"], cfg["D"], cfg["C"]
+        self.B, self.D, self.Cn = B, D, Cn
+        if B % world:
+            raise SystemExit("global batch must divide by the number of ranks")
+        self.b_local = B // world
+        # Inputs: generated once, on rank 0 (identical bits to what the oracle sees), then the
+        # embeddings / labels are broadcast and the class shards scattered on the device -- for
+        # C = 1,000,000 every rank generating 2 GB of weights itself would dominate the run.
+        self.inp = make_inputs(B, D, Cn) if rank == 0 else None
+        if world == 1:
+            self.Xfull, self.yfull = self.inp.X, self.inp.y
+            self.Xd, self.yd, self.Wd = self.inp.X.to(dev), self.inp.y.to(dev), self.inp.W.to(dev)
+            self.head = self.head_nv = None
+            self.lo, self.hi = 0, Cn
+        else:
+            from tf_face_toolbox_b200.sharded import shard_bounds
+            Xg = self.inp.X.to(dev) if rank == 0 else torch.empty(B, D, device=dev)
+            yg = self.inp.y.to(dev) if rank == 0 else torch.empty(B, dtype=torch.int32, device=dev)
+            dist.broadcast(Xg, 0)
+            dist.broadcast(yg, 0)
+            self.lo, self.hi = shard_bounds(Cn, world, rank)
+            per = -(-Cn // world)
+            mine = torch.zeros(D, per, device=dev)
+            if rank == 0:
+                Wg = self.inp.W.to(dev)
+                parts = []
+                for r in range(world):
+                    a, b = shard_bounds(Cn, world, r)
+                    t = torch.zeros(D, per, device=dev)
+                    t[:, :b - a] = Wg[:, a:b]
+                    parts.append(t)
+                dist.scatter(mine, parts, src=0)
+                del parts, Wg
+            else:
+                dist.scatter(mine, None, src=0)
+            Wshard = mine[:, :self.hi - self.lo].contiguous()
+            del mine
+            self.Xfull, self.yfull = Xg.cpu(), yg.cpu()
+            self.Xd = Xg[rank * self.b_local:(rank + 1) * self.b_local].contiguous()
+            self.yd = yg[rank * self.b_local:(rank + 1) * self.b_local].contiguous()
+            self.head = ShardedASoftmaxHead(D, Cn, m=M_MARGIN, mode=mode, device=dev, weights_shard=Wshard)
+            self.head_nv = None
+            if not args.no_nvlink:
+                try:
+                    self.head_nv = ShardedASoftmaxHead(D, Cn, m=M_MARGIN, mode=mode, device=dev, weights_shard=Wshard,
+                                                       transport="nvlink", batch_global=B)
+                    self.head_nv.step(self.Xd, self.yd, LAMBDA)
+                    torch.cuda.synchronize()
+                except Exception as e:      # pragma: no cover
+                    print(f"bench: nvlink transport unavailable ({type(e).__name__}: {e})", file=sys.stderr)
+                    self.head_nv = None
+                okt = torch.tensor([1 if self.head_nv is not None else 0], device=dev)
+                dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+                if int(okt.item()) == 0:
+                    self.head_nv = None
+            torch.cuda.empty_cache()
+        # config 5: the center loss (loss.py:29-45) on the same gathered batch, class-sharded like W
+        self.center = None
+        if center:
+            g = torch.Generator().manual_seed(4321)
+            full = torch.randn(Cn, D, generator=g) * 0.1        # same bits on every rank
+            cen = full[self.lo:self.hi].contiguous()
+            self.center = dict(centers=cen.to(dev), init=cen, init_full=full, alpha=0.95, weight=0.008)
+        self.need_flush = Cn * D * 4 <= 126e6
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if self.need_flush else None
+        self.paths, self.host_paths = {}, {}
+        self._build_paths()
+
+    # ---- launch paths --------------------------------------------------------------------
+    def _center_step(self, X, y, dX):
+        """Center loss of this shard's classes on the batch rows this rank holds the gradient of."""
+        from tf_face_toolbox_b200.center import center_loss
+        c = self.center
+        return center_loss(X, y, c["centers"], c["alpha"], c["weight"], class_offset=self.lo, grad_accum=dX)[0]
+
+    def _build_paths(self):
+        torch, dist = self.torch, self.dist
+        from tf_face_toolbox_b200 import GraphedASoftmaxStep, asoftmax_head
+        args, B, Cn, mode, world = self.args, self.B, self.Cn, self.mode, self.world
+        if world == 1:
+            def step():
+                loss, _, dX, dW = asoftmax_head(self.Xd, self.yd, Cn, M_MARGIN, LAMBDA, weights=self.Wd, mode=mode)
+                if self.center is not None:
+                    loss = (loss, self._center_step(self.Xd, self.yd, dX))
+                return loss, dX, dW
+        else:
+            def step():
+                if self.center is not None:
+                    return self.head.step(self.Xd, self.yd, LAMBDA, center=self.center)
+                return self.head.step(self.Xd, self.yd, LAMBDA)
+        self.paths["eager"] = step
+        if self.center is not None:
+            return                                   # config 5 is timed through the eager calls only
+
+        def try_capture(make):
+            g = None
+            if not args.no_graph:
+                try:
+                    g = make()
+                    g(self.Xd, self.yd)
+                    torch.cuda.synchronize()
+                except Exception as e:      # pragma: no cover
+                    print(f"bench: CUDA-graph capture unavailable ({type(e).__name__}: {e})", file=sys.stderr)
+                    g = None
+            if world > 1:
+                ok = torch.tensor([1 if g is not None else 0], device=self.dev)
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+                if int(ok.item()) == 0:
+                    g = None
+            return g
+
+        def make_graph_main():
+            if world == 1:
+                self.gstep = GraphedASoftmaxStep(self.Wd, batch_size=B, m=M_MARGIN, mode=mode)
+                return lambda X, y: self.gstep(X, y, LAMBDA)
+            self.head.capture(self.b_local)
+            return lambda X, y: self.head.step_graphed(X, y, LAMBDA)
+
+        def make_graph_nv():
+            self.head_nv.capture(self.b_local)
+            return lambda X, y: self.head_nv.step_graphed(X, y, LAMBDA)
+        graphed = try_capture(make_graph_main)
+        if graphed is not None:
+            self.paths["graph"] = lambda: graphed(self.Xd, self.yd)
+            self.host_paths["graph"] = graphed
+        if world > 1 and self.head_nv is not None:
+            self.paths["nvlink"] = lambda: self.head_nv.step(self.Xd, self.yd, LAMBDA)
+            graphed_nv = try_capture(make_graph_nv)
+            if graphed_nv is not None:
+                self.paths["nvlink_graph"] = lambda: graphed_nv(self.Xd, self.yd)
+                self.host_paths["nvlink_graph"] = graphed_nv
+
+    # ---- parity gate -----------------------------------------------------------------------
+    def parity(self):
+        """Every launch path, run once on the bench inputs, against the float64 oracle: loss on
+        every rank (identical bits across ranks), this rank's dX rows on every rank, dW on rank
+        0's class shard.  BASELINE.md: parity gates must pass before any number is reported."""
+        import numpy as np
+        torch, dist = self.torch, self.dist
+        from oracle import asoftmax_ref as ref
+        rank, world, B, D, Cn = self.rank, self.world, self.B, self.D, self.Cn
+        t0 = time.time()
+        ref_loss = torch.zeros(1, dtype=torch.float64)
+        ref_dX = torch.zeros(B, D, dtype=torch.float64)
+        ref_dW = None
+        ref_center = None
+        if rank == 0:
+            big = Cn >= 500000           # config 4: float32 matmuls inside the float64 streaming oracle
+            r = ref.asoftmax_head_streamed(self.inp.X.numpy(), self.inp.W.numpy(), self.inp.y.numpy(), M_MARGIN, LAMBDA,
+                                           chunk=16384, dw_ranges=[(self.lo, self.hi)],
+                                           dtype=np.float32 if big else np.float64)
+            ref_loss[0] = r.loss
+            ref_dX = torch.from_numpy(r.dX)
+            ref_dW = r.dW[(self.lo, self.hi)]
+        if world > 1:
+            rl, rx = ref_loss.to(self.dev), ref_dX.to(self.dev)
+            dist.broadcast(rl, 0)
+            dist.broadcast(rx, 0)
+            ref_loss, ref_dX = rl.cpu(), rx.cpu()
+        rows = slice(rank * self.b_local, (rank + 1) * self.b_local)
+        want_dX = ref_dX[rows].numpy()
+        if self.center is not None:
+            # oracle of the center loss on the whole batch (loss.py:29-45): total loss, the gradient
+            # it sends to every row, and the updated centers -- this rank checks its slice of each
+            closs_ref, cen_new, cgrad = ref.center_loss(self.Xfull.numpy(), self.yfull.numpy(),
+                                                        self.center["init_full"].numpy(),
+                                                        alpha=self.center["alpha"], weight=self.center["weight"])
+            ref_center = dict(loss=closs_ref, grad=cgrad, centers=cen_new[self.lo:self.hi])
+        out = {}
+        ok_all = True
+        for name, fn in self.paths.items():
+            if self.center is not None:
+                self.center["centers"].copy_(self.center["init"])
+            res = fn()
+            torch.cuda.synchronize()
+            loss, dX, dW = res[0], res[1], res[2]
+            closs = None
+            if isinstance(loss, tuple):
+                loss, closs = loss
+            loss = float(loss)
+            rec = {"loss_rel": abs(loss - float(ref_loss[0])) / abs(float(ref_loss[0]))}
+            dXn = dX.double().cpu().numpy()
+            if ref_center is not None:
+                # dX also carries the center-loss gradient of this rank's rows
+                rec["center_loss_rel"] = abs(float(closs) - ref_center["loss"]) / max(ref_center["loss"], 1e-30)
+                rec["center_update_max_abs"] = float(np.abs(self.center["centers"].double().cpu().numpy()
+                                                            - ref_center["centers"]).max())
+                rec["cos_dX"] = _cos(dXn, want_dX + ref_center["grad"][rows])
+            else:
+                rec["cos_dX"] = _cos(dXn, want_dX)
+            if rank == 0 and dW is not None:
+                rec["cos_dW"] = _cos(dW.double().cpu().numpy(), ref_dW)
+            ok = rec["loss_rel"] <= LOSS_TOL[self.mode] and rec["cos_dX"] >= COS_MIN and rec.get("cos_dW", 1.0) >= COS_MIN
+            if ref_center is not None:
+                ok = ok and rec["center_loss_rel"] <= 1e-4 and rec["center_update_max_abs"] <= 1e-5
+            if world > 1:
+                # same loss bits on every rank, and every rank's rows pass
+                t = torch.tensor([loss, -loss, rec["cos_dX"], 1.0 if ok else 0.0], device=self.dev, dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MIN)
+                rec["loss_identical_across_ranks"] = bool(float(t[0]) == -float(t[1]))
+                rec["cos_dX"] = float(t[2])                      # worst rank
+                ok = bool(float(t[3]) == 1.0) and rec["loss_identical_across_ranks"]
+            rec["ok"] = bool(ok)
+            ok_all = ok_all and rec["ok"]
+            out[name] = rec
+        return {"ok": bool(ok_all), "tolerance": {"loss_rel": LOSS_TOL[self.mode], "cos_min": COS_MIN},
+                "oracle": "oracle/asoftmax_ref.py::asoftmax_head_streamed (float64 statistics, "
+                          + ("float32" if Cn >= 500000 else "float64") + " matmuls)",
+                "checked": "loss and dX rows on every rank (worst rank reported), dW on rank 0's class shard",
+                "seconds": round(time.time() - t0, 2), "paths": out}
+
+    # ---- timing ----------------------------------------------------------------------------
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def timed(self, fn, n):
+        """n calls of fn between CUDA events on the current stream; returns ms (max over ranks)."""
+        torch = self.torch
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            if self.flush is not None:
+                self.flush.zero_()
+            fn()
+        e1.record()
+        self.barrier()
+        ms = e0.elapsed_time(e1)
+        if self.world > 1:
+            t = torch.tensor([ms], device=self.dev)
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    def flush_cost(self):
+        torch = self.torch
+        if self.flush is None:
+            return 0.0
+        for _ in range(3):
+            self.flush.zero_()
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(20):
+            self.flush.zero_()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / 20
+
+    def time_value(self, K, Wm):
+        """Device-resident timing of every launch path; the fastest is the headline."""
+        self.flush_ms = self.flush_cost()
+        value_ms = {}
+        for name, fn in self.paths.items():
+            for _ in range(max(Wm, 3)):
+                fn()
+            value_ms[name] = self.timed(fn, K) / K - self.flush_ms
+        best = min(value_ms, key=value_ms.get)
+        return best, value_ms
+
+    def close(self):
+        for hd in (self.head, self.head_nv):
+            for attr in ("_graph", "_gout"):
+                if hd is not None and hasattr(hd, attr):
+                    setattr(hd, attr, None)
+        if getattr(self, "gstep", None) is not None:
+            self.gstep.close()
+        self.paths.clear()
+        self.host_paths.clear()
+        self.head = self.head_nv = None
+        from tf_face_toolbox_b200.head import release_handles
+        release_handles()
+        self.Xd = self.yd = self.Wd = self.flush = None
+        self.torch.cuda.empty_cache()
 
 
 # ----------------------------------------------------------------------------------------
@@ -163,9 +467,9 @@ def workload_config(args, cfg, world):
 def run_ours(args, cfg):
     import torch
     import torch.distributed as dist
-    from tf_face_toolbox_b200 import GraphedASoftmaxStep, ShardedASoftmaxHead, asoftmax_head
+    from tf_face_toolbox_b200 import _lib
     from tf_face_toolbox_b200.head import get_handle
-    from tf_face_toolbox_b200.synthetic import make_inputs
+    from tf_face_toolbox_b200.synthetic import CONFIGS
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -176,155 +480,50 @@ def run_ours(args, cfg):
     dev = torch.device("cuda", local)
     # a stuck collective must not hang the caller: dump every thread's stack and exit
     import faulthandler
-    faulthandler.dump_traceback_later(float(os.environ.get("BENCH_WATCHDOG_S", "600")), exit=True)
+    faulthandler.dump_traceback_later(float(os.environ.get("BENCH_WATCHDOG_S", "900")), exit=True)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("BENCH_NCCL_DEBUG", "WARN")
+        # communicator lines (ranks, transports) go to stderr so that the driver can check them
+        os.environ.setdefault("NCCL_DEBUG", os.environ.get("BENCH_NCCL_DEBUG", "INFO"))
+        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
-    B, D, Cn, mode = cfg["B"], cfg["D"], cfg["C"], args.mode
+    mode = args.mode
     K, Wm = args.steps, args.warmup
     peaks = load_peaks()
     t_start = time.time()
-    inp = make_inputs(B, D, Cn)
-    flush = None
-    need_flush = Cn * D * 4 <= 126e6
-    if need_flush:
-        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    # anything that changes what the library does is part of the record
+    knobs = {k: v for k, v in sorted(os.environ.items()) if k.startswith("ASM_")}
+    bringup = "ASM_B200_LIB" in knobs or "ASM_UMMA_DEBUG" in knobs
+
+    def note(msg):
+        if rank == 0 and os.environ.get("BENCH_VERBOSE"):
+            print(f"[bench {time.time() - t_start:6.1f}s] {msg}", file=sys.stderr, flush=True)
+
+    def fail_parity(par, what):
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "value": None, "unit": UNIT, "n_gpus": world, "parity": par,
+                              "error": f"parity gate failed for {what}: no number is reported"}), flush=True)
+        sys.stdout.flush()
+        os._exit(3)
 
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
 
-    if world == 1:
-        Xd, yd, Wd = inp.X.to(dev), inp.y.to(dev), inp.W.to(dev)
+    wl = Workload(args, cfg, mode, rank, world, dev, center=bool(cfg.get("center")))
+    B, D, Cn, b_local = wl.B, wl.D, wl.Cn, wl.b_local
+    note("setup done, paths=%s" % list(wl.paths))
+    parity = wl.parity()
+    note("parity gate: %s (%.1fs)" % (parity["ok"], parity["seconds"]))
+    if not parity["ok"]:
+        fail_parity(parity, args.workload)
 
-        def step():
-            return asoftmax_head(Xd, yd, Cn, M_MARGIN, LAMBDA, weights=Wd, mode=mode)
-        b_local = B
-    else:
-        if B % world:
-            raise SystemExit("global batch must divide by the number of ranks")
-        b_local = B // world
-        head = ShardedASoftmaxHead(D, Cn, m=M_MARGIN, mode=mode, device=dev, weights_full=inp.W)
-        Xd = inp.X[rank * b_local:(rank + 1) * b_local].contiguous().to(dev)
-        yd = inp.y[rank * b_local:(rank + 1) * b_local].contiguous().to(dev)
-
-        def step():
-            return head.step(Xd, yd, LAMBDA)
-        # the same step with the collectives done by the head's own kernels over NVLink peer
-        # memory (no NCCL launch in the step)
-        head_nv = None
-        if not args.no_nvlink:
-            try:
-                head_nv = ShardedASoftmaxHead(D, Cn, m=M_MARGIN, mode=mode, device=dev, weights_full=inp.W,
-                                              transport="nvlink", batch_global=B)
-                head_nv.step(Xd, yd, LAMBDA)
-                torch.cuda.synchronize()
-            except Exception as e:      # pragma: no cover
-                print(f"bench: nvlink transport unavailable ({type(e).__name__}: {e})", file=sys.stderr)
-                head_nv = None
-            okt = torch.tensor([1 if head_nv is not None else 0], device=dev)
-            dist.all_reduce(okt, op=dist.ReduceOp.MIN)
-            if int(okt.item()) == 0:
-                head_nv = None
-
-    # CUDA-graph replay of the same step (one launch instead of 7 kernels / 3 collectives):
-    # the public GraphedASoftmaxStep / ShardedASoftmaxHead.capture API.  Falls back to the
-    # eager call if capture is not possible.
-    def try_capture(make):
-        g = None
-        if not args.no_graph:
-            try:
-                g = make()
-                g(Xd, yd)
-                torch.cuda.synchronize()
-            except Exception as e:      # pragma: no cover
-                print(f"bench: CUDA-graph capture unavailable ({type(e).__name__}: {e})", file=sys.stderr)
-                g = None
-        if world > 1:
-            ok = torch.tensor([1 if g is not None else 0], device=dev)
-            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-            if int(ok.item()) == 0:
-                g = None
-        return g
-
-    def make_graph_main():
-        if world == 1:
-            gstep = GraphedASoftmaxStep(Wd, batch_size=B, m=M_MARGIN, mode=mode)
-            return lambda X, y: gstep(X, y, LAMBDA)
-        head.capture(b_local)
-        return lambda X, y: head.step_graphed(X, y, LAMBDA)
-
-    def make_graph_nv():
-        head_nv.capture(b_local)
-        return lambda X, y: head_nv.step_graphed(X, y, LAMBDA)
-    graphed = try_capture(make_graph_main)
-    # each path: name -> (device-resident step, host-input step)
-    paths = {"eager": step}
-    host_paths = {}
-    if graphed is not None:
-        paths["graph"] = lambda: graphed(Xd, yd)
-        host_paths["graph"] = graphed
-    if world > 1 and head_nv is not None:
-        paths["nvlink"] = lambda: head_nv.step(Xd, yd, LAMBDA)
-        graphed_nv = try_capture(make_graph_nv)
-        if graphed_nv is not None:
-            paths["nvlink_graph"] = lambda: graphed_nv(Xd, yd)
-            host_paths["nvlink_graph"] = graphed_nv
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, n):
-        """n calls of fn between CUDA events on the current stream; returns ms (max over ranks)."""
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(n):
-            if flush is not None:
-                flush.zero_()
-            fn()
-        e1.record()
-        barrier()
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms
-
-    flush_ms = 0.0
-    if flush is not None:       # cost of the L2 flush itself, subtracted from flushed loops
-        for _ in range(3):
-            flush.zero_()
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(20):
-            flush.zero_()
-        e1.record()
-        torch.cuda.synchronize()
-        flush_ms = e0.elapsed_time(e1) / 20
-
-    def note(msg):
-        if rank == 0 and os.environ.get("BENCH_VERBOSE"):
-            print(f"[bench {time.time() - t_start:6.1f}s] {msg}", file=sys.stderr, flush=True)
-    note("setup done, graph=%s" % (graphed is not None))
     # ---- (1) device-resident timing: the headline `value`
-    # both launch paths are timed (W warm-up + K steps each); the faster one is the headline
-    # and the one used for the remaining load (eager wins when the GPU is the bottleneck,
-    # the graph when launch overhead is, i.e. at larger N)
     t_load0 = time.time()
-    value_ms = {}
-    for name, fn in paths.items():
-        for _ in range(max(Wm, 3)):
-            fn()
-        value_ms[name] = timed(fn, K) / K - flush_ms
-    value_path = min(value_ms, key=value_ms.get)
-    run_step = paths[value_path]
+    value_path, value_ms = wl.time_value(K, Wm)
+    run_step = wl.paths[value_path]
     ms_step = value_ms[value_path]
+    flush_ms = wl.flush_ms
     value = B / (ms_step * 1e-3)
 
     # distribution of the chosen path (SURVEY 8d asks for median and p10/p90): events between
@@ -333,97 +532,132 @@ def run_ours(args, cfg):
     grp = 5 if K >= 10 else 1
     ngrp = max(1, K // grp)
     evs = [torch.cuda.Event(enable_timing=True) for _ in range(ngrp + 1)]
-    barrier()
+    wl.barrier()
     for gi in range(ngrp):
         evs[gi].record()
         for _ in range(grp):
-            if flush is not None:
-                flush.zero_()
+            if wl.flush is not None:
+                wl.flush.zero_()
             run_step()
     evs[ngrp].record()
-    barrier()
+    wl.barrier()
     per = sorted(evs[i].elapsed_time(evs[i + 1]) / grp - flush_ms for i in range(ngrp))
     step_dist = {"p10": per[int(0.1 * (ngrp - 1))], "p50": per[(ngrp - 1) // 2],
                  "p90": per[int(round(0.9 * (ngrp - 1)))], "group": grp, "groups": ngrp,
                  "note": "rank-0 CUDA-event time per step over groups of `group` steps, same loop as value"}
-    note("value loop done: %.4f ms/step" % ms_step)
+    note("value loop done: %.4f ms/step (%s)" % (ms_step, value_path))
+
     # ---- (2) per-kernel durations (CUDA events on the launching stream, inside the library)
+    # of the transport the headline uses: the NVLink-transport handle when it won, else the plain one
     kernels = {}
-    h = get_handle(dev, D, Cn, Cn, 0, B, M_MARGIN, mode) if world == 1 else head.compute._handle(B)
+    if world == 1:
+        h = get_handle(dev, D, Cn, Cn, 0, B, M_MARGIN, mode)
+        prof_step = wl.paths["eager"]
+    elif value_path.startswith("nvlink") and wl.head_nv is not None:
+        h = wl.head_nv._p2p["handle"]
+        prof_step = wl.paths["nvlink"]
+    else:
+        h = wl.head.compute._handle(B)
+        prof_step = wl.paths["eager"]
+    prof_step()
     launches_per_step = int(h.lib.asm_last_launch_count(h.ptr))
+    if wl.center is not None:
+        launches_per_step += 2                      # center_loss_kernel + center_update_kernel
     h.lib.asm_set_profiling(h.ptr, 1)
     ms_buf = (C.c_float * 16)()
     names = C.create_string_buffer(16 * 32)
     for _ in range(K):
-        if flush is not None:
-            flush.zero_()
-        step()
+        if wl.flush is not None:
+            wl.flush.zero_()
+        prof_step()
         n = h.lib.asm_get_profile(h.ptr, 16, ms_buf, names)
         for i in range(max(n, 0)):
             nm = names.raw[i * 32:(i + 1) * 32].split(b"\0")[0].decode()
             kernels.setdefault(nm, []).append(ms_buf[i])
     h.lib.asm_set_profiling(h.ptr, 0)
     kavg = {k: sum(v) / len(v) for k, v in kernels.items()}
-
     note("profile loop done")
-    # ---- (3) end to end through the public Python API with HOST buffers
-    Xh = (inp.X if world == 1 else inp.X[rank * b_local:(rank + 1) * b_local]).contiguous().pin_memory()
-    yh = (inp.y if world == 1 else inp.y[rank * b_local:(rank + 1) * b_local]).contiguous().pin_memory()
+
+    # ---- (3) end to end with HOST buffers: H2D of the step's inputs and D2H of its results (the
+    # loss AND dX, the gradient the backbone consumes) inside the timed region, every step
+    Xh = wl.Xfull[rank * b_local:(rank + 1) * b_local].contiguous().pin_memory()
+    yh = wl.yfull[rank * b_local:(rank + 1) * b_local].contiguous().pin_memory()
     loss_h = torch.empty(1, dtype=torch.float32).pin_memory()
+    dX_h = torch.empty(b_local, D, dtype=torch.float32).pin_memory()
+
+    def first_loss(out):
+        l0 = out[0][0] if isinstance(out[0], tuple) else out[0]
+        return l0.reshape(1)
 
     def make_e2e(name):
-        if name in host_paths:                # graph steps copy their (host) inputs themselves
-            g = host_paths[name]
+        if name in wl.host_paths:                # graph steps copy their (host) inputs themselves
+            g = wl.host_paths[name]
 
             def fn():
                 out = g(Xh, yh)
-                loss_h.copy_(out[0].reshape(1), non_blocking=False)   # D2H read of the result (syncs)
+                dX_h.copy_(out[1], non_blocking=True)
+                loss_h.copy_(first_loss(out), non_blocking=False)     # D2H read of the results (syncs)
                 return out
         else:
-            dev_step = paths[name]
+            dev_step = wl.paths[name]
 
             def fn():
-                Xd.copy_(Xh, non_blocking=True)
-                yd.copy_(yh, non_blocking=True)
+                wl.Xd.copy_(Xh, non_blocking=True)
+                wl.yd.copy_(yh, non_blocking=True)
                 out = dev_step()
-                loss_h.copy_(out[0].reshape(1), non_blocking=False)
+                dX_h.copy_(out[1], non_blocking=True)
+                loss_h.copy_(first_loss(out), non_blocking=False)
                 return out
         return fn
     e2e_ms = {}
-    for name in paths:
+    for name in wl.paths:
         fn = make_e2e(name)
         for _ in range(3):
             fn()
-        e2e_ms[name] = timed(fn, K) / K - flush_ms
+        e2e_ms[name] = wl.timed(fn, K) / K - flush_ms
     # the same through the package's host input pipeline (HostPipelinedStep): every step still
-    # copies its inputs H2D and has its loss read D2H, but the copies overlap the previous
-    # step's kernels and the loss is read one step late, so the GPU never waits for the host
+    # copies its inputs H2D and has its loss and dX read D2H, but the copies overlap the
+    # neighbouring steps' kernels and the results are read one step late
     from tf_face_toolbox_b200.pipeline import HostPipelinedStep
-    for name in list(paths):
-        if name in host_paths:
+    from tf_face_toolbox_b200 import asoftmax_head
+    for name in list(wl.paths):
+        if name in wl.host_paths or wl.center is not None:
             continue                          # graph steps own their static input buffers
-        dev_step = paths[name]
-        src = head_nv if name == "nvlink" else (head if world > 1 else None)
-        ls = os.environ.get("BENCH_LOSS_STREAM", "0") == "1"      # opt-in A/B of the read-back stream
+        src = wl.head_nv if name == "nvlink" else (wl.head if world > 1 else None)
         if src is not None:
-            runner = HostPipelinedStep(lambda X, y, _h=src: _h.step(X, y, LAMBDA), b_local, D, dev,
-                                       loss_stream=ls)
+            runner = HostPipelinedStep(lambda X, y, _h=src: _h.step(X, y, LAMBDA), b_local, D, dev, read_dx=True)
         else:
             runner = HostPipelinedStep(lambda X, y: (lambda o: (o[0], o[2], o[3]))(
-                asoftmax_head(X, y, Cn, M_MARGIN, LAMBDA, weights=Wd, mode=mode)), b_local, D, dev,
-                loss_stream=ls)
+                asoftmax_head(X, y, Cn, M_MARGIN, LAMBDA, weights=wl.Wd, mode=mode)), b_local, D, dev, read_dx=True)
 
         def fn(_r=runner):
             return _r.submit(Xh, yh)
         for _ in range(3):
             fn()
         runner.flush()
-        e2e_ms[name + "_pipelined"] = timed(lambda: (fn()), K) / K - flush_ms
+        e2e_ms[name + "_pipelined"] = wl.timed(lambda: (fn()), K) / K - flush_ms
         runner.flush()
+    # ... and through the reference-shaped drop-in surface: forward / loss_function / gradients of
+    # the Network-shaped wrapper (nets/net_base.py:84-107, data_parallel.py:220-236)
+    if world == 1 and wl.center is None:
+        from tf_face_toolbox_b200 import ASoftmaxHead, LambdaState
+        net = ASoftmaxHead(D, Cn, m=M_MARGIN, mode=mode, device=dev, lambda_state=LambdaState(explicit=LAMBDA))
+        net.weights = wl.Wd
+
+        def fn_net():
+            wl.Xd.copy_(Xh, non_blocking=True)
+            wl.yd.copy_(yh, non_blocking=True)
+            out = net.forward(wl.Xd, wl.yd, num_classes=Cn, is_training=True)
+            losses, _names, _others = net.loss_function("TOWER_0", wl.yd, **out)
+            dXn, _dWn = net.gradients()
+            dX_h.copy_(dXn, non_blocking=True)
+            loss_h.copy_((losses[0] + losses[1]).reshape(1), non_blocking=False)
+        for _ in range(3):
+            fn_net()
+        e2e_ms["network_api"] = wl.timed(fn_net, K) / K - flush_ms
     note("e2e loops done")
     e2e_path = min(e2e_ms, key=e2e_ms.get)
     ms_e2e = e2e_ms[e2e_path]
-    t_load1 = time.time()
     e2e_value = B / (ms_e2e * 1e-3)
 
     # keep the GPU under the same load long enough for nvidia-smi to sample clocks; the
@@ -437,96 +671,137 @@ def run_ours(args, cfg):
         done += 50
         torch.cuda.synchronize()
     t_load1 = time.time()
-    note("extra-load loop done (%d steps)" % n_extra)
     clocks = sampler.stop(t_load0, t_load1) if rank == 0 else None
-    note("clock sampler stopped")
     if world > 1:
         dist.barrier()
-    note("final barrier passed")
+    note("main workload done")
+
+    line = None
+    if rank == 0:
+        line = build_line(args, cfg, world, mode, peaks, kavg, value, ms_step, value_path, value_ms, step_dist,
+                          e2e_value, ms_e2e, e2e_path, e2e_ms, b_local, launches_per_step, K, Wm, clocks, parity,
+                          knobs, bringup, _lib.load().asm_version().decode(), "graph" in wl.paths or "nvlink_graph" in wl.paths)
+    wl.close()
+    del wl
+
+    # ---- (4) config 4 in the same process (C = 1,000,000, batch 1024): the configuration the
+    # north star's ">= 6x at 8 GPUs" is stated on, same version, same box, parity-gated
+    if args.workload == "cfg3" and not args.no_cfg4:
+        cfg4 = dict(CONFIGS["cfg4"])
+        note("config 4 ...")
+        w4 = Workload(args, cfg4, cfg4["mode"], rank, world, dev)
+        par4 = w4.parity()
+        note("config 4 parity: %s (%.1fs)" % (par4["ok"], par4["seconds"]))
+        if not par4["ok"]:
+            fail_parity(par4, "cfg4")
+        K4 = max(5, min(K, 20))
+        p4, ms4 = w4.time_value(K4, 3)
+        if rank == 0:
+            line["cfg4"] = {"workload": "cfg4: A-softmax head fwd+bwd, C=1000000 D=512 batch=1024 m=4 lambda=5.0 bf16",
+                            "value": cfg4["B"] / (ms4[p4] * 1e-3), "unit": UNIT, "ms_per_step": ms4[p4], "steps": K4,
+                            "value_path": p4, "ms_per_step_by_path": ms4, "n_gpus": world, "scaling": "strong",
+                            "parity": par4,
+                            "step_algorithmic_tflops": 6.0 * cfg4["B"] * cfg4["D"] * cfg4["C"] / (ms4[p4] * 1e-3) / 1e12}
+        w4.close()
+        del w4
 
     if rank == 0:
-        C_local = Cn if world == 1 else -(-Cn // world)
-        gemm_flops = 2.0 * B * D * C_local
-        roof_kernels = []
-        Cp_l = (C_local + 255) // 256 * 256
-        for nm, ms in kavg.items():
-            if nm == "dw_gemm" and mode == "bf16":
-                # HBM is the binding roofline of the dW kernel: it reads G'' and Wb (bf16) and
-                # writes dW (fp32): 351 MB at cfg 3 = 54 us at the measured copy bandwidth,
-                # against 28 us of tensor time for its 2*B*D*C flops
-                by = 2.0 * B * Cp_l + 2.0 * D * Cp_l + 4.0 * D * C_local
-                ach = by / (ms * 1e-3) / 1e9
-                roof_kernels.append({"kernel": nm, "ms": ms, "bound": "hbm", "achieved": ach, "unit": "GB/s",
-                                     "frac": ach / peaks["hbm"],
-                                     "tensor_tflops": gemm_flops / (ms * 1e-3) / 1e12})
-            elif nm in ("fwd_logits_stats", "bwd_recompute_g", "dw_gemm", "dx_gemm"):
-                ach = gemm_flops / (ms * 1e-3) / 1e12
-                roof_kernels.append({"kernel": nm, "ms": ms, "bound": "tensor", "achieved": ach, "unit": "TFLOP/s",
-                                     "frac": ach / peaks["tf_burst"]})
-            elif nm == "prep_norms":
-                Cp = (C_local + 255) // 256 * 256
-                by = 4.0 * D * C_local + (2.0 * D * Cp if mode == "bf16" else 0) + 4.0 * B * D
-                ach = by / (ms * 1e-3) / 1e9
-                roof_kernels.append({"kernel": nm, "ms": ms, "bound": "hbm", "achieved": ach, "unit": "GB/s",
-                                     "frac": ach / peaks["hbm"]})
-            else:
-                roof_kernels.append({"kernel": nm, "ms": ms})
-        dom = max((k for k in roof_kernels if "bound" in k), key=lambda k: k["ms"], default=None)
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "traffic_cfg3.json")
-        if world == 1 and args.workload == "cfg3" and mode == "bf16" and os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get("kernels", {})
-        roofline = None
-        if dom is not None:
-            roofline = {"kernel": dom["kernel"], "bound": dom["bound"], "achieved": dom["achieved"],
-                        "peak": peaks["tf_burst"] if dom["bound"] == "tensor" else peaks["hbm"],
-                        "unit": dom["unit"], "frac": dom["frac"],
-                        "traffic": (traffic or {}).get(dom["kernel"]),
-                        "peak_source": peaks["src"] + (" burst bf16" if dom["bound"] == "tensor" else " copy"),
-                        "ms": dom["ms"]}
-        step_flops = 6.0 * B * D * Cn
-        line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(Wm, 3),
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": mode, "data": "synthetic", "config": workload_config(args, cfg, world),
-            "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e, "path": e2e_path,
-                    "ms_per_step_by_path": e2e_ms,
-                    "h2d_bytes_per_step": int(b_local * D * 4 + b_local * 4), "d2h_bytes_per_step": 4},
-            "gpu_launches": launches_per_step * K,
-            "cuda_graph": graphed is not None, "value_path": value_path, "ms_per_step_by_path": value_ms,
-            "ms_per_step_dist": step_dist,
-            "roofline": roofline,
-            "step_tensor_frac": step_flops / (ms_step * 1e-3) / 1e12 / peaks["tf_burst"],
-            "step_algorithmic_tflops": step_flops / (ms_step * 1e-3) / 1e12,
-            "kernels": roof_kernels,
-        }
         if world == 1 and not args.no_cpu_baseline:
             r = time_cpu_port(cfg, 8, 1, budget_s=25.0)
             line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
                                     "sample": r["sample"]}
         print(json.dumps(line), flush=True)
-    # teardown must never turn a finished measurement into a hang: drop the captured graphs
-    # first (NCCL work captured in a live graph can block destroy_process_group) and bail out
-    # with success if the process group still does not come down
+    # teardown must never turn a finished measurement into a hang
     sys.stdout.flush()
     faulthandler.cancel_dump_traceback_later()
     if world > 1:
         bail = threading.Timer(20.0, lambda: os._exit(0))
         bail.daemon = True
         bail.start()
-        graphed = None
-        run_step = None
-        paths.clear()
-        host_paths.clear()
-        for hd in (head, head_nv):
-            for attr in ("_graph", "_gout"):
-                if hd is not None and hasattr(hd, attr):
-                    setattr(hd, attr, None)
         torch.cuda.synchronize()
         dist.barrier()
         dist.destroy_process_group()
         bail.cancel()
+
+
+def build_line(args, cfg, world, mode, peaks, kavg, value, ms_step, value_path, value_ms, step_dist, e2e_value,
+               ms_e2e, e2e_path, e2e_ms, b_local, launches_per_step, K, Wm, clocks, parity, knobs, bringup, version,
+               has_graph):
+    B, D, Cn = cfg["B"], cfg["D"], cfg["C"]
+    C_local = Cn if world == 1 else -(-Cn // world)
+    Cp_l = (C_local + 255) // 256 * 256
+    gemm_flops = 2.0 * B * D * C_local
+    roof_kernels = []
+    for nm, ms in kavg.items():
+        t = ms * 1e-3
+        if nm == "dw_gemm":
+            # SURVEY 8(d) algorithmic work of the dW contraction: 2 B D C flop and ONE fp32 write of
+            # dW (4 D C bytes).  What the kernel's plan additionally reads (G'' and the bf16 weights
+            # for the normalisation-Jacobian term) is reported separately, not credited.
+            alg = 4.0 * D * C_local
+            plan = alg + (2.0 * B * Cp_l + 2.0 * D * Cp_l if mode == "bf16" else 0.0)
+            roof_kernels.append({"kernel": nm, "ms": ms, "bound": "hbm", "achieved": alg / t / 1e9, "unit": "GB/s",
+                                 "frac": alg / t / 1e9 / peaks["hbm"], "algorithmic_bytes": alg,
+                                 "plan_bytes": plan, "plan_gbs": plan / t / 1e9,
+                                 "tensor_tflops": gemm_flops / t / 1e12,
+                                 "tensor_frac": gemm_flops / t / 1e12 / peaks["tf_burst"]})
+        elif nm in ("fwd_logits_stats", "bwd_recompute_g", "dx_gemm"):
+            ach = gemm_flops / t / 1e12
+            roof_kernels.append({"kernel": nm, "ms": ms, "bound": "tensor", "achieved": ach, "unit": "TFLOP/s",
+                                 "frac": ach / peaks["tf_burst"]})
+        elif nm == "prep_norms":
+            by = 4.0 * D * C_local + (2.0 * D * Cp_l if mode == "bf16" else 0) + 4.0 * B * D
+            ach = by / t / 1e9
+            roof_kernels.append({"kernel": nm, "ms": ms, "bound": "hbm", "achieved": ach, "unit": "GB/s",
+                                 "frac": ach / peaks["hbm"], "algorithmic_bytes": by})
+        else:
+            roof_kernels.append({"kernel": nm, "ms": ms})
+    dom = max((k for k in roof_kernels if "bound" in k), key=lambda k: k["ms"], default=None)
+    # DRAM traffic per launch comes from an ncu capture (profiles/), never from this run; it is only
+    # quoted when that capture was taken from the same library version and workload
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic_cfg3.json")
+    traffic_note = None
+    if world == 1 and args.workload == "cfg3" and mode == "bf16" and os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        if tj.get("library_version") == version:
+            traffic = tj.get("kernels", {})
+        else:
+            traffic_note = f"profiles/traffic_cfg3.json is for '{tj.get('library_version')}', this library is '{version}'"
+    roofline = None
+    if dom is not None:
+        roofline = {"kernel": dom["kernel"], "bound": dom["bound"], "achieved": dom["achieved"],
+                    "peak": peaks["tf_burst"] if dom["bound"] == "tensor" else peaks["hbm"],
+                    "unit": dom["unit"], "frac": dom["frac"],
+                    "traffic": (traffic or {}).get(dom["kernel"]),
+                    "traffic_source": "profiles/traffic_cfg3.json (ncu, same library version)" if traffic else traffic_note,
+                    "peak_source": peaks["src"] + (" burst bf16" if dom["bound"] == "tensor" else " copy"),
+                    "ms": dom["ms"]}
+        for k in ("algorithmic_bytes", "plan_bytes", "plan_gbs", "tensor_frac"):
+            if k in dom:
+                roofline[k] = dom[k]
+    step_flops = 6.0 * B * D * Cn
+    transport = ("nvlink-p2p (the head's own kernels over peer memory, no collective launch)"
+                 if value_path.startswith("nvlink") else ("nccl (3 collectives per step)" if world > 1 else "none"))
+    return {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(Wm, 3),
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": mode, "data": "synthetic", "config": workload_config(args, cfg, world),
+        "parity": parity, "transport": transport,
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e, "path": e2e_path,
+                "ms_per_step_by_path": e2e_ms,
+                "h2d_bytes_per_step": int(b_local * D * 4 + b_local * 4),
+                "d2h_bytes_per_step": int(b_local * D * 4 + 4)},
+        "gpu_launches": launches_per_step * K, "launches_per_step": launches_per_step,
+        "cuda_graph": has_graph, "value_path": value_path, "ms_per_step_by_path": value_ms,
+        "ms_per_step_dist": step_dist,
+        "roofline": roofline,
+        "step_tensor_frac": step_flops / (ms_step * 1e-3) / 1e12 / peaks["tf_burst"],
+        "step_algorithmic_tflops": step_flops / (ms_step * 1e-3) / 1e12,
+        "kernels": roof_kernels,
+        "library": version, "env": knobs, "bringup_build": bringup,
+    }
 
 
 def main():
@@ -542,6 +817,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="time the eager per-kernel launches")
     ap.add_argument("--graph", action="store_true", help="(default) also time the CUDA-graph replay of the step")
     ap.add_argument("--no-nvlink", action="store_true", help="N>1: skip the NVLink peer-memory transport")
+    ap.add_argument("--no-cfg4", action="store_true", help="skip the config-4 (C = 1M) sub-record of the cfg3 line")
     args = ap.parse_args()
     cfg = dict(CONFIGS[args.workload])
     if args.mode is None:

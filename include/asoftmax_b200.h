@@ -198,6 +198,20 @@ int asm_step_p2p(asm_head* h, const float* X_local, int32_t b_local, const void*
 int asm_p2p_set_timeout(asm_head* h, int32_t milliseconds);
 int asm_p2p_status(asm_head* h, void* cuda_stream);
 
+/*
+ * Gradient transform and regularisation loss, at no extra pass over [D, C].  The reference's
+ * towers differentiate total_loss = cross_entropy + reg_loss and scale every gradient by
+ * mult_lr / num_gpus (data_parallel.py:32-38, :224; reg_loss = wd/2 |W|^2 from the contrib
+ * l2_regularizer, nets/sphere.py:88, nets/net_base.py:103-107).  Once set, every step call
+ * returns  dX := grad_scale * dX,  dW := grad_scale * (dW + weight_decay * W)  (the scale rides in
+ * the softmax-gradient offset, the weight-decay term in the dW epilogue's per-class coefficient)
+ * and, when reg_loss_out is not NULL, writes  weight_decay/2 * sum over this shard's classes of
+ * |w_j|^2  to that device float (the column sums of squares are a by-product of the norm kernel;
+ * deterministic).  loss_out stays the unscaled cross-entropy.  Defaults: 1, 0, NULL.  With a
+ * fused optimizer armed the optimizer's own weight_decay applies instead of this one.
+ */
+int asm_set_gradient_transform(asm_head* h, float grad_scale, float weight_decay, float* reg_loss_out);
+
 /* CUDA-graph support.  Kernel arguments are frozen when a step is captured into a graph, so
  * lambda (which anneals per step) can instead be read from a caller-owned DEVICE float:
  * once set (non-NULL) it overrides the by-value `lambda` argument of every step call; NULL

@@ -330,8 +330,18 @@ def test_fused_optimizer_matches_unfused_update(kind, mode):
         assert cosine(upd_f, upd_r) >= cos_min, (step, cosine(upd_f, upd_r))
         # fp32: same arithmetic up to rounding.  bf16: the fused epilogue projects with the fp32
         # master weight, the unfused one with its bf16 copy (2^-9 relative on that term)
-        tol = 2e-3 if mode == "fp32" else (3e-2 if kind == "Momentum" else 2.0)
-        np.testing.assert_allclose(upd_f, upd_r, rtol=0, atol=tol * np.abs(upd_r).max())
+        if not (kind == "Adam" and mode == "bf16"):
+            tol = 2e-3 if mode == "fp32" else 3e-2
+            np.testing.assert_allclose(upd_f, upd_r, rtol=0, atol=tol * np.abs(upd_r).max())
+        else:
+            # Adam's first steps are sign-like (m / sqrt(v) = +-1), so an element whose gradient is
+            # near zero may flip between the two projections and move by 2 lr; everywhere else the
+            # updates agree.  Bound the flips instead of waving every element through: at most
+            # 2 % of the elements may differ by more than 10 % of the step, none by more than 2 lr.
+            diff = np.abs(upd_f - upd_r)
+            step_sz = np.abs(upd_r).max()
+            assert diff.max() <= 2.05 * step_sz
+            assert (diff > 0.1 * step_sz).mean() <= 0.02, (diff > 0.1 * step_sz).mean()
     # the plain path is unaffected afterwards (optimizer disarmed): dW is returned again
     _, _, _, dW2 = asoftmax_head(X, y, Cn, 4, 5.0, weights=W_f, mode=mode)
     assert dW2 is not None
@@ -426,3 +436,137 @@ def test_sharded_head_fused_optimizer_matches_single_call(mode):
     torch.testing.assert_close(o1.state0, o2.state0, rtol=1e-5, atol=1e-10)
     torch.testing.assert_close(dX1, dX2, rtol=1e-5, atol=1e-9)
     assert not torch.equal(W, inp.W.to(dev))                      # the weights did move
+
+
+# ------------------------------------------------------------------------- round 2 additions
+def test_fused_optimizer_on_cuda_core_path_keeps_dx(monkeypatch):
+    """with the CUDA-core fp32 kernels the dX kernel reads the fp32 weights the fused
+    optimizer rewrites; dX must equal the unfused call's dX bit for bit (dX runs first there)."""
+    from tf_face_toolbox_b200 import FusedOptimizer
+    monkeypatch.setenv("ASM_FP32_SIMT", "1")
+    dev = torch.device("cuda:0")
+    B, D, Cn = 96, 128, 2000
+    inp = make_inputs(B, D, Cn, seed=43)
+    X, y = inp.X.to(dev), inp.y.to(dev)
+    W = inp.W.to(dev)
+    _, _, dX_plain, dW_plain = asoftmax_head(X, y, Cn, 4, 5.0, weights=W, mode="fp32", _handle_tag="simt-opt")
+    Wf = W.clone()
+    opt = FusedOptimizer("Momentum", lr=0.5, weight_decay=0.0)         # a large step: a race would show
+    for _ in range(3):
+        Wf.copy_(W)
+        opt.state0 = None
+        _, _, dX_fused, none_dW = asoftmax_head(X, y, Cn, 4, 5.0, weights=Wf, mode="fp32", optimizer=opt,
+                                                _handle_tag="simt-opt")
+        assert none_dW is None
+        torch.cuda.synchronize()
+        assert torch.equal(dX_fused, dX_plain)
+    torch.testing.assert_close(Wf, W - 0.5 * dW_plain, rtol=1e-5, atol=1e-9)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_gradient_transform_and_reg_loss_cost_no_pass(mode):
+    """grad_scale / weight_decay / reg_loss_out (asm_set_gradient_transform): what the towers do
+    to the gradients (data_parallel.py:32-38: tf.gradients(cross_entropy + reg_loss) * mult_lr /
+    num_gpus; nets/net_base.py:103-107) applied inside the kernels."""
+    dev = torch.device("cuda:0")
+    B, D, Cn = 192, 128, 3002                     # C % 4 == 2: the shifted odd-row dW boxes
+    inp = make_inputs(B, D, Cn, seed=51)
+    r = ref.asoftmax_head(inp.X.numpy(), inp.W.numpy(), inp.y.numpy(), 4, 5.0)
+    gs, wd = 0.125, 5e-4
+    reg = torch.zeros(1, device=dev)
+    loss, _, dX, dW = asoftmax_head(inp.X.to(dev), inp.y.to(dev), Cn, 4, 5.0, weights=inp.W.to(dev), mode=mode,
+                                    grad_scale=gs, weight_decay=wd, reg_loss_out=reg)
+    torch.cuda.synchronize()
+    assert abs(float(loss) - r.loss) <= LOSS_TOL[mode] * r.loss            # the loss itself is not scaled
+    assert float(reg) == pytest.approx(0.5 * wd * float((inp.W.double() ** 2).sum()), rel=1e-5)
+    want_dW = gs * (r.dW + wd * inp.W.double().numpy())
+    assert cosine(dX.cpu().numpy(), gs * r.dX) >= 0.9999
+    assert cosine(dW.cpu().numpy(), want_dW) >= 0.9999
+    tol = 2e-5 if mode == "fp32" else 2e-2
+    np.testing.assert_allclose(dX.cpu().numpy(), gs * r.dX, rtol=0, atol=tol * np.abs(gs * r.dX).max())
+    np.testing.assert_allclose(dW.cpu().numpy(), want_dW, rtol=0, atol=tol * np.abs(want_dW).max())
+    # the handle is back to the defaults afterwards
+    _, _, dX1, dW1 = asoftmax_head(inp.X.to(dev), inp.y.to(dev), Cn, 4, 5.0, weights=inp.W.to(dev), mode=mode)
+    assert cosine(dW1.cpu().numpy(), r.dW) >= 0.9999 and abs(float(dX1.abs().max()) / np.abs(r.dX).max() - 1) < 0.05
+
+
+def test_network_wrapper_makes_no_eager_pass_over_weights():
+    """loss_function / gradients of the Network-shaped wrapper take reg_loss
+    and the scaled, weight-decayed gradients straight from the kernels."""
+    dev = torch.device("cuda:0")
+    inp = make_inputs(64, 128, 500, seed=8)
+    head = ASoftmaxHead(128, 500, m=4, mode="fp32", device=dev, num_gpus=4, mult_lr=2.0,
+                        lambda_state=LambdaState(explicit=5.0))
+    head.weights.copy_(inp.W.to(dev))
+    out = head.forward(inp.X.to(dev), inp.y.to(dev), num_classes=500, is_training=True)
+    losses, names, _ = head.loss_function("TOWER_0", inp.y.to(dev), **out)
+    dX, dW = head.gradients()
+    r = ref.asoftmax_head(inp.X.numpy(), inp.W.numpy(), inp.y.numpy(), 4, 5.0)
+    assert names == ["cross_entropy", "reg_loss"]
+    assert float(losses[1]) == pytest.approx(0.5 * 5e-4 * float((inp.W.double() ** 2).sum()), rel=1e-5)
+    np.testing.assert_allclose(dX.cpu().numpy(), 0.5 * r.dX, rtol=2e-3, atol=1e-5 * np.abs(r.dX).max())
+    np.testing.assert_allclose(dW.cpu().numpy(), 0.5 * (r.dW + 5e-4 * inp.W.numpy()), rtol=2e-3,
+                               atol=1e-5 * np.abs(r.dW).max())
+    dX1, dW1 = head.gradients(num_gpus=1, mult_lr=1.0)             # another scale: rescaled on request
+    np.testing.assert_allclose(dX1.cpu().numpy(), r.dX, rtol=2e-3, atol=1e-5 * np.abs(r.dX).max())
+
+
+def test_out_of_range_label_poisons_the_loss():
+    """a label outside [0, C) must not yield a finite-but-wrong loss when nobody asks
+    asm_check_labels: the row's loss is NaN (as TF's sparse softmax CE yields on the GPU)."""
+    inp = make_inputs(32, 64, 100, seed=5)
+    dev = torch.device("cuda:0")
+    y = inp.y.clone()
+    y[3] = 100
+    loss, *_ = asoftmax_head(inp.X.to(dev), y.to(dev), 100, 4, 5.0, weights=inp.W.to(dev), mode="fp32")
+    assert np.isnan(float(loss))
+    loss, *_ = asoftmax_head(inp.X.to(dev), inp.y.to(dev), 100, 4, 5.0, weights=inp.W.to(dev), mode="fp32")
+    assert np.isfinite(float(loss))
+
+
+def test_bf16_cfg5_full_size_vs_streamed_oracle():
+    """BASELINE config 5, head part at full size: C = 85,742, D = 512, batch 2048, bf16."""
+    dev = torch.device("cuda:0")
+    B, D, Cn = 2048, 512, 85742
+    inp = make_inputs(B, D, Cn)
+    r = ref.asoftmax_head_streamed(inp.X.numpy(), inp.W.numpy(), inp.y.numpy(), 4, 5.0, chunk=8192,
+                                   dw_ranges=[(0, 4096), (40000, 44096), (Cn - 3000, Cn)], dtype=np.float32)
+    loss, _, dX, dW = asoftmax_head(inp.X.to(dev), inp.y.to(dev), Cn, 4, 5.0, weights=inp.W.to(dev), mode="bf16",
+                                    check_labels=True)
+    torch.cuda.synchronize()
+    assert abs(float(loss) - r.loss) <= 2e-3 * r.loss
+    assert cosine(dX.cpu().numpy(), r.dX) >= 0.9999
+    for (lo, hi), want in r.dW.items():
+        assert cosine(dW[:, lo:hi].cpu().numpy(), want) >= 0.9999, (lo, hi)
+
+
+def test_bf16_cfg4_shard_geometry_vs_streamed_oracle():
+    """A config-4 shard at full size: batch 1024, D = 512, C_local = 125,000 (the 1/8 shard of
+    C = 1,000,000), here as two such shards of a 250,000-class problem run one after the other
+    through asm_forward_partial / asm_backward_partial and combined like the exchange would."""
+    from tf_face_toolbox_b200.sharded import _CudaShard, shard_bounds
+    dev = torch.device("cuda:0")
+    B, D, Cn, G = 1024, 512, 250000, 2
+    inp = make_inputs(B, D, Cn, seed=404)
+    r = ref.asoftmax_head_streamed(inp.X.numpy(), inp.W.numpy(), inp.y.numpy(), 4, 5.0, chunk=16384,
+                                   dw_ranges=[(0, 8192), (125000, 125000 + 8192), (Cn - 4096, Cn)], dtype=np.float32)
+    X, y = inp.X.to(dev), inp.y.to(dev)
+    shards = []
+    for g in range(G):
+        lo, hi = shard_bounds(Cn, G, g)
+        assert hi - lo == 125000
+        shards.append((_CudaShard(D, Cn, lo, hi, 4, "bf16", g, G, dev), inp.W[:, lo:hi].contiguous().to(dev), lo, hi))
+    stats_all = torch.stack([sh.forward_partial(X, y, Wg, 5.0) for sh, Wg, _, _ in shards]).contiguous()
+    dX = torch.zeros(B, D, device=dev)
+    dWs, losses = {}, []
+    for sh, Wg, lo, hi in shards:
+        loss, dXp, dWg = sh.backward_partial(stats_all, X, Wg)
+        dX += dXp
+        dWs[lo] = dWg
+        losses.append(float(loss))
+    torch.cuda.synchronize()
+    assert losses[0] == losses[1] and abs(losses[0] - r.loss) <= 2e-3 * r.loss
+    assert cosine(dX.cpu().numpy(), r.dX) >= 0.9999
+    for (lo, hi), want in r.dW.items():
+        base = 0 if lo < 125000 else 125000
+        assert cosine(dWs[base][:, lo - base:hi - base].cpu().numpy(), want) >= 0.9999, (lo, hi)

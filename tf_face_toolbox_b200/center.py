@@ -32,6 +32,9 @@ def center_loss(features: torch.Tensor, labels: torch.Tensor, centers: torch.Ten
     X = features.contiguous()
     y = labels.contiguous()
     B, D = X.shape
+    if grad_accum is not None and not (grad_accum.is_cuda and grad_accum.dtype == torch.float32
+                                       and grad_accum.is_contiguous() and tuple(grad_accum.shape) == (B, D)):
+        raise TypeError("grad_accum must be a contiguous CUDA float32 tensor of the features' shape [B, D]")
     lib = _lib.load()
     grad = grad_accum if grad_accum is not None else torch.zeros_like(X)
     loss = torch.empty(1, device=X.device, dtype=torch.float32)

@@ -62,7 +62,7 @@ size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct Layout {
   size_t ylocal, flags, n, inv_n, inv_c, tgt_s, tgt_f, part, stats_local, lse, negoff, gtarget, rcoef, rowloss, counter,
-      q_part, G, dx_part, Xb, Wb, Xg, step_dev, total;
+      q_part, G, dx_part, Xb, Wb, Xg, step_dev, wsq_part, wsq_ticket, total;
   int Cp, NT, MT;
   size_t dx_capacity;
 };
@@ -124,8 +124,10 @@ Layout make_layout(const asm_config& c, int num_sms) {
   L.rcoef = take(B * 4);
   L.rowloss = take(B * 4);
   L.counter = take(256);
+  L.wsq_part = take(((size_t)L.Cp / 32 + 16) * 4);    // one partial per W-role block of the norm kernel
+  L.wsq_ticket = take(256);
   L.q_part = take((size_t)L.MT * L.Cp * 4);
-  L.G = take(B * (size_t)L.Cp * (c.mode == ASM_MODE_BF16 ? 2 : 4));
+  L.G = take(align_up(B, 64) * (size_t)L.Cp * (c.mode == ASM_MODE_BF16 ? 2 : 4));   // fp32 mode: two bf16 planes, or fp32 on the CUDA-core path
   L.dx_part = take(L.dx_capacity * 4);
   if (tc) {
     L.Xb = take(planes * B * D * 2);
@@ -187,12 +189,19 @@ int run_forward(asm_head* h, const float* X, int B, const void* labels, int labe
   s.B = B;
   s.lambda = lambda;
   s.invB = 1.0f / (float)B;
+  s.Bp = (int)align_up((size_t)B, 64);
   s.X = X;
   s.W = W;
   s.logits = logits;
   s.l2_hints = (h->tune.l2_hints & 1) ? 1 : 0;
-  s.MT = h->tc ? umma_q_parts(B, umma_tile_width(h->tune, (h->tune.cg_mask & 2) ? 2 : 1))
-               : (B + kRowTileHost - 1) / kRowTileHost;
+  {
+    // BWDG geometry: class tiles of 256 (per CTA pair) x batch tiles; it writes one q partial per
+    // column half of a batch tile
+    const int bcg = (h->tune.cg_mask & 2) ? 2 : 1;
+    const long long bunits = (long long)(s.Cp / (128 * bcg)) * ((B + 255) / 256);
+    s.MT = h->tc ? umma_q_parts(B, umma_tile_width(h->tune, bcg, bunits, h->num_sms))
+                 : (B + kRowTileHost - 1) / kRowTileHost;
+  }
   h->launches = 0;
   h->n_marks = 0;
   {
@@ -224,7 +233,9 @@ int run_forward(asm_head* h, const float* X, int B, const void* labels, int labe
     {
       const int fcg = (h->tune.cg_mask & 1) ? 2 : 1;
       // narrow tiles only with CTA pairs, and the forward pairs need at least two row tiles
-      s.NT = umma_forward_tiles(B, s.Cp, h->num_sms, fcg, umma_tile_width(h->tune, (fcg == 2 && B > 128) ? 2 : 1));
+      const int ecg = (fcg == 2 && B > 128) ? 2 : 1;
+      const long long funits = (long long)(((B + 127) / 128 + ecg - 1) / ecg) * (s.Cp / 256);
+      s.NT = umma_forward_tiles(B, s.Cp, h->num_sms, fcg, umma_tile_width(h->tune, ecg, funits, h->num_sms));
     }
     s.KS = umma_dx_splits(B, s.D, s.Cp, h->num_sms, (h->tune.cg_mask & 8) ? 2 : 1);
     if (h->maps_B != B) {
@@ -332,7 +343,7 @@ int run_backward(asm_head* h, const float* stats_all, int n_shards, float* loss_
 
 extern "C" {
 
-const char* asm_version(void) { return "asoftmax_b200 0.1 sm_100a"; }
+const char* asm_version(void) { return "asoftmax_b200 0.2 sm_100a"; }
 
 float asm_lambda(int64_t iteration, float base, float gamma, float power, float lambda_min) {
   const double v = (double)base * pow(1.0 + (double)gamma * (double)iteration, -(double)power);
@@ -441,6 +452,12 @@ int asm_create(asm_head** out, const asm_config* cfg) {
   s.rowloss = (float*)(w + L.rowloss);
   s.counter = (unsigned int*)(w + L.counter);
   s.q_part = (float*)(w + L.q_part);
+  s.wsq_part = (float*)(w + L.wsq_part);
+  s.wsq_ticket = (unsigned int*)(w + L.wsq_ticket);
+  s.gscale = 1.0f;
+  s.wd_g = 0.0f;
+  s.reg_scale = 0.0f;
+  s.reg_out = nullptr;
   s.G = (void*)(w + L.G);
   s.dx_part = (float*)(w + L.dx_part);
   h->dx_part_capacity = L.dx_capacity;
@@ -649,6 +666,18 @@ int asm_set_optimizer(asm_head* h, const asm_optimizer* opt, float* state0, floa
   }
   s.opt_s0 = state0;
   s.opt_s1 = state1;
+  return ASM_OK;
+}
+
+int asm_set_gradient_transform(asm_head* h, float grad_scale, float weight_decay, float* reg_loss_out) {
+  if (!h) return ASM_ERR_INVALID_ARG;
+  if (!(weight_decay >= 0.f) || !(grad_scale == grad_scale))
+    return fail(h, ASM_ERR_INVALID_ARG, "bad grad_scale / weight_decay%s", "");
+  Step& s = h->st;
+  s.gscale = grad_scale;
+  s.wd_g = grad_scale * weight_decay;
+  s.reg_scale = 0.5f * weight_decay;
+  s.reg_out = reg_loss_out;
   return ASM_OK;
 }
 

@@ -107,6 +107,15 @@ struct Step {
   int B, D, C, Cp, C_total, class_offset, m, mode;
   float lambda, invB;
   const float* lambda_dev;   // optional device scalar overriding `lambda` (CUDA-graph replay)
+  // gradient transform (asm_set_gradient_transform): dX, dW come out as
+  // gscale * (d loss / d.) and dW additionally carries gscale * weight_decay * W -- what
+  // tf.gradients(cross_entropy + reg_loss) * mult_lr / num_gpus yields (data_parallel.py:32-38)
+  float gscale;              // 1 by default
+  float wd_g;                // gscale * weight_decay (0 by default)
+  float reg_scale;           // 0.5 * weight_decay: reg_loss = reg_scale * ||W||^2 (contrib l2_regularizer)
+  float* reg_out;            // device scalar receiving reg_loss of this shard's classes, or null
+  float* wsq_part;           // [W-role blocks of the norm kernel] partial sums of w^2
+  unsigned int* wsq_ticket;  // [1]
   // caller buffers (device)
   const float* X;            // [B, D]
   const float* W;            // [D, C]
@@ -133,7 +142,8 @@ struct Step {
   unsigned int* counter;     // [1]   last-block-done ticket of the combine kernel
   float* q_part;             // [MT, Cp] column sums  sum_i G'_ij s_ij per 128-row group
   int MT;
-  void* G;                   // [B, Cp]  G'' = G' * inv_c   (fp32 or bf16 by mode)
+  void* G;                   // G'' = G' * inv_c: tcgen05 paths bf16 CLASS-major [Cp, Bp] ([Cp, 2Bp] when x3); CUDA-core path fp32 [B, Cp]
+  int Bp;                    // batch pitch of the class-major G'': B rounded up to 64
   float* dx_part;            // [KS, B, D] split-K partials of dX
   int KS;
   __nv_bfloat16* Xb;         // [B, D]    bf16 mode;  [B, 3D]  (three planes side by side) when x3
@@ -197,7 +207,7 @@ struct UmmaTuning {          // MN-major shared-memory descriptor parameters (by
   uint32_t mn_lbo, mn_sbo, mn_kstep;
   uint32_t cg_mask;          // CTA pairs (cta_group::2) per kernel: bit0 FWD, bit1 BWDG, bit2 DW, bit3 DX
   uint32_t debug_flags;      // bit0: skip epilogue math, bit1: DW without stores, bit2: X-resident forward variant (ASM_UMMA_DEBUG, bring-up only)
-  uint32_t bn;               // tile width along N of FWD / BWDG / DW: 0 or 256 = default, 128 = narrow (ASM_UMMA_BN)
+  uint32_t bn;               // tile width along N of FWD / BWDG / DW: 0 = chosen per launch from the unit count, 128, 256 (ASM_UMMA_BN)
   uint32_t l2_order;         // consecutive kernels sweep the classes in opposite directions (ASM_L2_ORDER=0 disables)
   uint32_t dw_tma;           // dW leaves through shared memory + TMA stores (ASM_DW_TMA=0: direct stores)
   uint32_t l2_hints;         // evict-first on single-use streams: bit0 the fp32 W read of the norm kernel, bit1 the dW stores (ASM_L2_HINTS)
@@ -221,7 +231,8 @@ cudaError_t umma_configure();
 bool umma_build_maps(UmmaMaps* m, const Step& s);
 // (re-)encode the dW store maps for this step's output buffer; sets m->dw_ok
 void umma_build_dw_maps(UmmaMaps* m, const Step& s);
-int umma_tile_width(const UmmaTuning& tu, int cg);
+// tile width along N of a CTA-pair kernel with `units256` 256-wide work units (0 / auto, 128 or 256 by tu.bn)
+int umma_tile_width(const UmmaTuning& tu, int cg, long long units256, int num_sms);
 int umma_forward_tiles(int B, int Cp, int num_sms, int cg, int bn = 256);
 int umma_forward_grid(int B, int Cp, int num_sms, int cg, int bn = 256);
 int umma_q_parts(int B, int bn = 256);

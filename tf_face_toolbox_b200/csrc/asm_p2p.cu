@@ -138,10 +138,17 @@ __global__ void __launch_bounds__(256) dx_finish_p2p_kernel(Step s, P2P p) {
   const size_t n4 = (size_t)p.b_local * s.D / 4;
   const size_t row0 = (size_t)p.rank * p.b_local * s.D / 4;
   for (size_t i = vb * (size_t)256 + threadIdx.x; i < n4; i += (size_t)nred * 256) {
-    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int g = 0; g < p.world; ++g) {
-      const float4 v = __ldcv(reinterpret_cast<const float4*>(p.dx(g, cur & 1)) + row0 + i);
-      a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    // all peers' contributions are requested before the first add: one NVLink round trip per
+    // element instead of one per peer; the sum still runs in rank order (deterministic)
+    float4 v[kMaxPeers];
+#pragma unroll
+    for (int g = 0; g < kMaxPeers; ++g)
+      v[g] = g < p.world ? __ldcv(reinterpret_cast<const float4*>(p.dx(g, cur & 1)) + row0 + i)
+                         : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 a = v[0];
+#pragma unroll
+    for (int g = 1; g < kMaxPeers; ++g) {
+      if (g < p.world) { a.x += v[g].x; a.y += v[g].y; a.z += v[g].z; a.w += v[g].w; }
     }
     reinterpret_cast<float4*>(p.dx_local)[i] = a;
   }

@@ -110,6 +110,29 @@ __global__ void __launch_bounds__(256) prep_kernel(Step s, const void* labels, i
       for (int r = 0; r < TY; ++r) acc += red[r][t];
       const int j = bid * 2 * TX + t;
       if (j < s.Cp) s.inv_c[j] = (j < s.C && acc > 0.f) ? rsqrtf(acc) : 0.f;
+      if (s.reg_out) red[0][t] = j < s.C ? acc : 0.f;
+    }
+    if (s.reg_out) {
+      // reg_loss = wd/2 * sum_j c_j^2 (nets/net_base.py:103-107) falls out of the column sums:
+      // one partial per block, totalled in a fixed order by the last W-role block to finish
+      __syncthreads();
+      if (tid == 0) {
+        float tot = 0.f;
+        for (int t = 0; t < 2 * TX; ++t) tot += red[0][t];
+        s.wsq_part[bid] = tot;
+      }
+      if (block_ticket(s.wsq_ticket, (unsigned)nwb) == (unsigned)nwb - 1) {
+        __shared__ float wred[256];
+        float acc = 0.f;
+        for (int i = tid; i < nwb; i += 256) acc += __ldcg(s.wsq_part + i);
+        wred[tid] = acc;
+        __syncthreads();
+        for (int o = 128; o > 0; o >>= 1) {
+          if (tid < o) wred[tid] += wred[tid + o];
+          __syncthreads();
+        }
+        if (tid == 0) *s.reg_out = s.reg_scale * wred[0];
+      }
     }
   } else {
     const int tx = tid & 31;
@@ -132,8 +155,7 @@ __global__ void __launch_bounds__(256) prep_kernel(Step s, const void* labels, i
                            : (long long)reinterpret_cast<const int*>(labels)[row];
     }
     float acc = 0.f;
-    for (int d = tx; d < s.D; d += 32) {
-      const float v = npub > 0 ? __ldcv(x + d) : __ldg(x + d);
+    auto emit = [&](int d, float v) {               // one element: norm, gathered copy, bf16 planes
       if (npub > 0) xg[d] = v;
       acc = fmaf(v, v, acc);
       if (PL > 0) {
@@ -146,6 +168,29 @@ __global__ void __launch_bounds__(256) prep_kernel(Step s, const void* labels, i
           r -= __bfloat162float(hv);
         }
       }
+    };
+    if (npub > 0) {
+      // a peer's row: every load is an NVLink round trip, so up to 4 x 16 bytes per lane (a row
+      // of D <= 512) are requested back to back before the first value is used
+      const float4* x4 = reinterpret_cast<const float4*>(x);
+      const int n4 = s.D / 4;                        // D % 16 == 0
+      for (int i0 = 0; i0 < n4; i0 += 128) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = i0 + u * 32 + tx;
+          v[u] = i < n4 ? __ldcv(x4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = i0 + u * 32 + tx;
+          if (i < n4) {
+            emit(4 * i, v[u].x); emit(4 * i + 1, v[u].y); emit(4 * i + 2, v[u].z); emit(4 * i + 3, v[u].w);
+          }
+        }
+      }
+    } else {
+      for (int d = tx; d < s.D; d += 32) emit(d, __ldg(x + d));
     }
     acc = warp_sum(acc);
     if (tx == 0) {

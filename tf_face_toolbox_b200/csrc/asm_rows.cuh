@@ -19,14 +19,15 @@ __device__ __forceinline__ void row_epilogue(const Step& s, int row, float m, fl
   const bool owned = yl_row >= 0;
   const float lse = m + logf(z);
   s.lse[row] = lse;
-  s.negoff[row] = -lse * 1.4426950408889634f + log2f(s.invB);
+  const float gB = s.invB * s.gscale;            // every gradient carries 1/B and the caller's scale
+  s.negoff[row] = -lse * 1.4426950408889634f + log2f(gB);
   s.rowloss[row] = yl_row == -2 ? __int_as_float(0x7fc00000) : lse - fy;
   float gt = 0.f, r = 0.f;
   if (owned) {
     float psi, dpsi;
     const float t = fminf(1.f, fmaxf(-1.f, tgt_s_row * inv_n_row));
     psi_eval(t, s.m, psi, dpsi);
-    const float gy = (expf(tgt_f_row - lse) - 1.0f) * s.invB;
+    const float gy = (expf(tgt_f_row - lse) - 1.0f) * gB;
     const float lam = step_lambda(s.lambda, s.lambda_dev);
     const float il = 1.0f / (1.0f + lam);
     gt = gy * (lam + dpsi) * il;

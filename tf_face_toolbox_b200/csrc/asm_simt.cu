@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(256) simt_kernel(Step s, int k_per_split) {
         if (d < s.D) {
           const size_t o = (size_t)d * s.C + j;
           if (s.opt.kind == 0) {
-            s.dW[o] = acc[a][b] - __ldg(s.W + o) * coef;
+            s.dW[o] = acc[a][b] - __ldg(s.W + o) * (coef - s.wd_g);
           } else {                              // fused optimizer: W updated in place
             float w = s.Wmut[o], s0 = s.opt_s0[o], s1 = s.opt.kind == 2 ? s.opt_s1[o] : 0.f;
             opt_apply(s.opt, acc[a][b] - w * coef, w, s0, s1);

@@ -11,8 +11,11 @@
 //   KIND   D (lanes x columns)          A (M x K)                  B (N x K)
 //   FWD    S   [batch x classes] K=D    Xb [B,D]   K-major         Wb [D,Cp]  MN-major
 //   BWDG   S^T [classes x batch] K=D    Wb [D,Cp]  MN-major        Xb [B,D]   K-major
-//   DW     dW^T[classes x d]     K=B    G''[B,Cp]  MN-major        Xb [B,D]   MN-major
-//   DX     dX  [batch x d]       K=C    G''[B,Cp]  K-major         Wb [D,Cp]  K-major (split-K)
+//   DW     dW^T[classes x d]     K=B    G''[Cp,Bp] K-major         Xb [B,D]   MN-major
+//   DX     dX  [batch x d]       K=C    G''[Cp,Bp] MN-major        Wb [D,Cp]  K-major (split-K)
+// G'' = G' diag(1/c) is kept CLASS-major ([Cp, Bp], batch contiguous): the recompute kernel's
+// threads own a class each, so their 32 batch values of a chunk are 64 contiguous bytes -- four
+// 16-byte shared-memory stores into a 64B-swizzled staging block that one TMA store writes out.
 // The orientation is chosen per kernel so that every reduction is thread-local and every
 // global store is coalesced: in FWD a thread owns a batch row (online max / sum-exp over the
 // classes in its registers); in BWDG and DW a thread owns a class (the column sums q_j and
@@ -47,7 +50,7 @@ constexpr int NUM_THREADS = 384;
 constexpr int EPI_THREADS = 256;
 constexpr int AUX_BARS = 512;                  // barriers + tmem ptr
 constexpr int AUX_VEC = 3 * 2 * BN * 4;        // per-tile vectors: 3 arrays x 2 stages x 256
-constexpr int STG_HALF = 32 * 128 * 2;         // G'' staging per column half: 32 rows x 128 classes
+constexpr int STG_HALF = 32 * 128 * 2;         // G'' staging per column half: 128 classes x 32 batch rows (bf16)
 constexpr int AUX_STG = 2 * STG_HALF;          // 16 KB
 constexpr int WB_BUF = 32 * 128 * 2;           // DW: one [32 d x 128 classes] bf16 weight chunk
 constexpr int AUX_WB = 2 * 2 * WB_BUF;         // 2 column halves x 2 buffers = 32 KB
@@ -145,7 +148,7 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
   constexpr int RES_B = G_::RES_B, CH_B = G_::CH_B, PIPE_B = G_::PIPE_B;
   constexpr bool IS_DW = (KIND == U_DW || KIND == U_DWOPT || KIND == U_DWF);
   constexpr bool IS_BWDG = (KIND == U_BWDG || KIND == U_BWDG1);
-  constexpr bool A_MN = (IS_BWDG || IS_DW);
+  constexpr bool A_MN = (IS_BWDG || KIND == U_DX);
   constexpr bool B_MN = (IS_FWD || IS_DW);
   constexpr bool N_FAST = (IS_BWDG || IS_DW);   // tile order: n index fastest
   extern __shared__ uint8_t smem_raw[];
@@ -617,23 +620,35 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
           };
           if (hit) body(std::true_type{}); else body(std::false_type{});
           // x3: G'' leaves as two bf16 planes (value, then the rounding residual), side by side
+          // along the batch dimension.  The thread's 32 batch values of this chunk are one 64-byte
+          // row of the class-major staging block [128 classes][32 batch]: four 16-byte stores, the
+          // 16-byte chunks XOR-swizzled by the row (CU_TENSOR_MAP_SWIZZLE_64B) so that the eight
+          // lanes of a store phase hit eight different bank groups.
           const int npl = s.x3 ? 2 : 1;
+          const int rsw = (lane_row >> 1) & 3;
 #pragma unroll 1
           for (int pl = 0; pl < npl; ++pl) {
             uint8_t* sbuf = stg_half + (NSB == 2 ? ((c * npl + pl) & 1) * STG_HALF : 0);
-            unsigned short* stgh = reinterpret_cast<unsigned short*>(sbuf) + lane_row;
+            uint4* rowp = reinterpret_cast<uint4*>(sbuf + lane_row * 64);
             if (leader) ptx::bulk_wait_read0();               // earlier stores have drained their buffers
             if (NSB == 1) named_bar_sync(2 + half, 128);
+            uint32_t pk[16];
 #pragma unroll
-            for (int b = 0; b < 32; ++b) {
-              const __nv_bfloat16 hv = __float2bfloat16_rn(gq[b]);
-              stgh[b * 128] = __bfloat16_as_ushort(hv);
-              if (npl > 1) gq[b] -= __bfloat162float(hv);
+            for (int b = 0; b < 16; ++b) {
+              const __nv_bfloat162 hv = __floats2bfloat162_rn(gq[2 * b], gq[2 * b + 1]);
+              pk[b] = *reinterpret_cast<const uint32_t*>(&hv);
+              if (npl > 1) {
+                gq[2 * b] -= __low2float(hv);
+                gq[2 * b + 1] -= __high2float(hv);
+              }
             }
+#pragma unroll
+            for (int qd = 0; qd < 4; ++qd)
+              rowp[qd ^ rsw] = make_uint4(pk[4 * qd], pk[4 * qd + 1], pk[4 * qd + 2], pk[4 * qd + 3]);
             ptx::fence_proxy_async();                         // generic writes -> async proxy
             named_bar_sync(2 + half, 128);
-            if (leader) {
-              ptx::tma_store_2d(&mapC, sbuf, m0 + pl * s.Cp, ib);
+            if (leader && ib < s.Bp) {                        // chunks past the padded batch hold nothing
+              ptx::tma_store_2d(&mapC, sbuf, ib + pl * s.Bp, m0);
               ptx::bulk_commit();
             }
           }
@@ -650,7 +665,7 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
         // d/2, column (d & 1) C + j); columns >= C are clipped by the tensor extent.
         const int j = m0 + lane_row;
         const bool jv = j < s.C;
-        const float coef = -(((pre0 + pre1) + (pre3 + pre4)) + pre5) * pre2 * pre2;
+        const float coef = fmaf(-(((pre0 + pre1) + (pre3 + pre4)) + pre5) * pre2, pre2, s.wd_g);   // + gscale * wd * W
         prefetch_tile(u + npairs);
         const int d_first = n0 + col0;
         const bool dw_tma = G_::DW_TMA && g.dw_tma;
@@ -728,7 +743,7 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
         // with the fp32 weights read straight from global memory (coalesced along j).
         const int j = m0 + lane_row;
         const bool jv = j < s.C;
-        const float coef = -(((pre0 + pre1) + (pre3 + pre4)) + pre5) * pre2 * pre2;
+        const float coef = fmaf(-(((pre0 + pre1) + (pre3 + pre4)) + pre5) * pre2, pre2, s.wd_g);   // + gscale * wd * W
         prefetch_tile(u + npairs);
         const int d_first = n0 + col0;
         ptx::mbar_wait(&tfull[a], aph);
@@ -871,7 +886,8 @@ EncodeTiledFn get_encode_fn() {
 
 // bf16 row-major [outer, inner] tensor with `pitch` elements per row; box = {box_inner, box_outer}
 bool encode_map(CUtensorMap* m, const void* base, uint64_t inner, uint64_t outer, uint64_t pitch,
-                uint32_t box_inner, uint32_t box_outer, bool swizzle128 = true, bool f32 = false) {
+                uint32_t box_inner, uint32_t box_outer, bool swizzle128 = true, bool f32 = false,
+                bool swizzle64 = false) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return false;
   cuuint64_t dims[2] = {inner, outer};
@@ -881,7 +897,8 @@ bool encode_map(CUtensorMap* m, const void* base, uint64_t inner, uint64_t outer
   return fn(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
             const_cast<void*>(base), dims, strides, box,
             estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-            swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+            swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                       : (swizzle64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE),
             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 }  // namespace
@@ -894,7 +911,18 @@ static int fwd_cg(int B, int cg) { return (cg == 2 && B > BM) ? 2 : 1; }
 // Tile width along N of FWD (classes), BWDG (batch rows) and DW (d): 256, or 128 when the
 // tuning asks for it and the kernel runs as CTA pairs.  (Narrow tiles double the number of
 // work units; see DESIGN.md section 9, wave quantisation on small shards.)
-int umma_tile_width(const UmmaTuning& tu, int cg) { return (tu.bn == 128 && cg == 2) ? 128 : BN_FULL; }
+int umma_tile_width(const UmmaTuning& tu, int cg, long long units256, int num_sms) {
+  if (cg != 2) return BN_FULL;                 // narrow tiles exist for the CTA-pair kernels only
+  if (tu.bn == 128) return 128;
+  if (tu.bn == 256) return BN_FULL;
+  // auto: rounds x width over the CTA pairs, with 128-wide rounds charged 15 % extra (half the
+  // operand reuse, twice the per-tile overhead -- measured: at 670 units the 256-wide tiles win
+  // by 9 %, at 84 units (a 1/8 shard of config 3) the 128-wide ones do)
+  const long long pairs = num_sms / 2;
+  const long long r256 = (units256 + pairs - 1) / pairs * 256;
+  const long long r128 = (2 * units256 + pairs - 1) / pairs * 128;
+  return (double)r128 * 1.15 < (double)r256 ? 128 : BN_FULL;
+}
 
 // FWD grid: a multiple of the number of row tiles so each CTA keeps one set of rows
 int umma_forward_grid(int B, int Cp, int num_sms, int cg, int bn) {
@@ -930,7 +958,8 @@ bool umma_build_maps(UmmaMaps* m, const Step& s) {
   // x3: the bf16 planes of each operand lie side by side along the inner dimension
   const uint64_t xd = (uint64_t)(s.x3 ? 3 : 1) * s.D;      // Xb [B, D] or [B, 3D]
   const uint64_t wc = (uint64_t)(s.x3 ? 3 : 1) * s.Cp;     // Wb [D, Cp] or [D, 3Cp]
-  const uint64_t gc = (uint64_t)(s.x3 ? 2 : 1) * s.Cp;     // G'' [B, Cp] or [B, 2Cp]
+  const uint64_t gp = (uint64_t)(s.x3 ? 2 : 1) * s.Bp;     // G'' pitch: [Cp, Bp] or [Cp, 2Bp] (two planes)
+  const uint64_t gi = s.x3 ? gp : (uint64_t)s.B;           // inner extent (batch): clipped at B, planes at Bp
   ok &= encode_map(&m->xb_k, s.Xb, xd, s.B, xd, 64, 128);     // A of FWD  (K-major, M = batch)
   ok &= encode_map(&m->xb_k256, s.Xb, xd, s.B, xd, 64, 256);  // B of BWDG (K-major, N = batch)
   ok &= encode_map(&m->xb_mn, s.Xb, xd, s.B, xd, 64, 64);     // B of DW   (MN-major, N = d)
@@ -938,9 +967,9 @@ bool umma_build_maps(UmmaMaps* m, const Step& s) {
   ok &= encode_map(&m->wb_mn32, s.Wb, wc, s.D, wc, 64, 32);   // B of FWDR (32-deep K stages)
   ok &= encode_map(&m->wb_k, s.Wb, wc, s.D, wc, 64, 256);     // B of DX   (K-major, N = d)
   ok &= encode_map(&m->wb_k128, s.Wb, wc, s.D, wc, 64, 128);  // B half of DX in a CTA pair
-  ok &= encode_map(&m->g_k, s.G, gc, s.B, gc, 64, 128);       // A of DX   (K-major, M = batch)
-  ok &= encode_map(&m->g_mn, s.G, gc, s.B, gc, 64, 64);       // A of DW   (MN-major, M = class)
-  ok &= encode_map(&m->g_st, s.G, gc, s.B, gc, 128, 32, false);    // BWDG store (no swizzle)
+  ok &= encode_map(&m->g_k, s.G, gi, s.Cp, gp, 64, 128);      // A of DW   (K-major: K = batch, M = class)
+  ok &= encode_map(&m->g_mn, s.G, gi, s.Cp, gp, 64, 64);      // A of DX   (MN-major: M = batch, K = class)
+  ok &= encode_map(&m->g_st, s.G, gi, s.Cp, gp, 32, 128, false, false, true);   // BWDG store (64B swizzle)
   ok &= encode_map(&m->wb_box, s.Wb, wc, s.D, wc, 128, 32, false); // DW weight chunks
   return ok;
 }
@@ -1057,7 +1086,7 @@ void launch_umma_forward(const Step& s, const UmmaMaps& m, const UmmaTuning& tu,
   UmmaArgs g = base_args(tu);   // S = Xb Wb: lanes = batch rows, columns = classes
   const int cg = fwd_cg(s.B, (tu.cg_mask & 1) ? 2 : 1);
   g.mt = ((s.B + BM - 1) / BM + cg - 1) / cg;
-  const int bn = umma_tile_width(tu, cg);
+  const int bn = umma_tile_width(tu, cg, (long long)g.mt * (s.Cp / BN_FULL), num_sms);
   g.nt = s.Cp / bn;
   const int units = umma_forward_grid(s.B, s.Cp, num_sms, cg, bn) / cg;
   if (bn == 128) {              // narrow tiles: more units for shards that do not fill the pairs
@@ -1092,7 +1121,7 @@ void launch_umma_bwdg(const Step& s, const UmmaMaps& m, const UmmaTuning& tu, in
   UmmaArgs g = base_args(tu);   // recompute S^T -> G'' (bf16) + q_part: lanes = classes
   const int cg = (tu.cg_mask & 2) ? 2 : 1;
   g.mt = s.Cp / (BM * cg);
-  const int bn = umma_tile_width(tu, cg);
+  const int bn = umma_tile_width(tu, cg, (long long)g.mt * ((s.B + BN_FULL - 1) / BN_FULL), num_sms);
   g.nt = (s.B + bn - 1) / bn;
   // A = weights, B = embeddings: the same plane pairs with the roles swapped
   set_segments(g, s.x3 != 0, (s.D + BK - 1) / BK, kSegLo, kSegHi, x3_segments(), s.Cp, s.D);
@@ -1111,32 +1140,32 @@ void launch_umma_dw(const Step& s, const UmmaMaps& m, const UmmaTuning& tu, int 
   UmmaArgs g = base_args(tu);   // dW^T = G''^T Xb - correction: lanes = classes, columns = d
   const int cg = (tu.cg_mask & 4) ? 2 : 1;
   g.mt = s.Cp / (BM * cg);
-  const int bn = umma_tile_width(tu, cg);
+  const int bn = umma_tile_width(tu, cg, (long long)g.mt * ((s.D + BN_FULL - 1) / BN_FULL), num_sms);
   g.nt = (s.D + bn - 1) / bn;
   set_segments(g, s.x3 != 0, (s.B + BK - 1) / BK, kSegG, kSegO, x3_segments() < 5 ? x3_segments() : 5,
-               s.Cp, s.D);
+               s.Bp, s.D);
   const int units = min(g.mt * g.nt, num_sms / cg);
   // upwards again (BWDG went down): the first class tiles are the ones BWDG wrote last
   g.dw_tma = (tu.dw_tma && cg == 2 && s.opt.kind == 0 && !s.x3 && m.dw_ok && m.dw_ptr == s.dW) ? 1 : 0;
   g.dw_shift = (s.C & 3) ? 2 : 0;
   g.store_evict_first = (tu.l2_hints & 2) ? 1 : 0;
   if (bn == 128) {
-    if (s.opt.kind != 0) launch_k<U_DWOPT, 2, 128>(units, m.g_mn, m.xb_mn, m.wb_box, s, g, st);
-    else if (s.x3) launch_k<U_DWF, 2, 128>(units, m.g_mn, m.xb_mn, m.wb_box, s, g, st);
-    else launch_k<U_DW, 2, 128>(units, m.g_mn, m.xb_mn, m.wb_box, s, g, st, &m.dw_even, &m.dw_odd);
+    if (s.opt.kind != 0) launch_k<U_DWOPT, 2, 128>(units, m.g_k, m.xb_mn, m.wb_box, s, g, st);
+    else if (s.x3) launch_k<U_DWF, 2, 128>(units, m.g_k, m.xb_mn, m.wb_box, s, g, st);
+    else launch_k<U_DW, 2, 128>(units, m.g_k, m.xb_mn, m.wb_box, s, g, st, &m.dw_even, &m.dw_odd);
     return;
   }
   if (s.opt.kind == 0 && s.x3) {
-    if (cg == 2) launch_k<U_DWF, 2>(units, m.g_mn, m.xb_mn, m.wb_box, s, g, st);
-    else launch_k<U_DWF, 1>(units, m.g_mn, m.xb_mn, m.wb_box, s, g, st);
+    if (cg == 2) launch_k<U_DWF, 2>(units, m.g_k, m.xb_mn, m.wb_box, s, g, st);
+    else launch_k<U_DWF, 1>(units, m.g_k, m.xb_mn, m.wb_box, s, g, st);
     return;
   }
   if (s.opt.kind != 0) {
-    if (cg == 2) launch_k<U_DWOPT, 2>(units, m.g_mn, m.xb_mn, m.wb_box, s, g, st);
-    else launch_k<U_DWOPT, 1>(units, m.g_mn, m.xb_mn, m.wb_box, s, g, st);
+    if (cg == 2) launch_k<U_DWOPT, 2>(units, m.g_k, m.xb_mn, m.wb_box, s, g, st);
+    else launch_k<U_DWOPT, 1>(units, m.g_k, m.xb_mn, m.wb_box, s, g, st);
   } else {
-    if (cg == 2) launch_k<U_DW, 2>(units, m.g_mn, m.xb_mn, m.wb_box, s, g, st, &m.dw_even, &m.dw_odd);
-    else launch_k<U_DW, 1>(units, m.g_mn, m.xb_mn, m.wb_box, s, g, st);
+    if (cg == 2) launch_k<U_DW, 2>(units, m.g_k, m.xb_mn, m.wb_box, s, g, st, &m.dw_even, &m.dw_odd);
+    else launch_k<U_DW, 1>(units, m.g_k, m.xb_mn, m.wb_box, s, g, st);
   }
 }
 
@@ -1147,7 +1176,7 @@ void launch_umma_dx(const Step& s, const UmmaMaps& m, const UmmaTuning& tu, int 
   g.mt = ((s.B + BM - 1) / BM + cg - 1) / cg;
   g.nt = (s.D + BN - 1) / BN;
   set_segments(g, s.x3 != 0, (s.Cp + BK - 1) / BK, kSegG, kSegO, x3_segments() < 5 ? x3_segments() : 5,
-               s.Cp, s.Cp);
+               s.Bp, s.Cp);
   g.ks = s.KS;
   g.kb_per = (g.kb_total + g.ks - 1) / g.ks;
   if (tu.l2_order && !s.x3) {   // all splits sweep the classes together, downwards (DW went up)
@@ -1155,8 +1184,8 @@ void launch_umma_dx(const Step& s, const UmmaMaps& m, const UmmaTuning& tu, int 
     g.rev = 1;
   }
   const int units = min(g.mt * g.nt * g.ks, num_sms / cg);
-  if (cg == 2) launch_k<U_DX, 2>(units, m.g_k, m.wb_k128, m.wb_k128, s, g, st);
-  else launch_k<U_DX, 1>(units, m.g_k, m.wb_k, m.wb_k, s, g, st);
+  if (cg == 2) launch_k<U_DX, 2>(units, m.g_mn, m.wb_k128, m.wb_k128, s, g, st);
+  else launch_k<U_DX, 1>(units, m.g_mn, m.wb_k, m.wb_k, s, g, st);
 }
 
 }  // namespace asmh

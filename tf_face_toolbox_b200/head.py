@@ -19,6 +19,7 @@ stream.  There is no CPU fallback.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from collections import OrderedDict
 from dataclasses import dataclass
 from typing import Dict, Optional, Tuple
@@ -94,7 +95,12 @@ class _Handle:
             pass
 
 
-_HANDLES: Dict[tuple, _Handle] = {}
+# Handles hold a device workspace (>= 200 MB at BASELINE config 3), so the cache is bounded:
+# untagged handles (plain asoftmax_head calls) are evicted least-recently-used beyond
+# ASM_MAX_HANDLES; tagged handles belong to the object that made them (a CUDA-graph step, a
+# sharded head) and are dropped with it (drop_handle).
+_HANDLES: "OrderedDict[tuple, _Handle]" = OrderedDict()
+_MAX_HANDLES = int(os.environ.get("ASM_MAX_HANDLES", "8"))
 
 
 def _round_batch(B: int) -> int:
@@ -111,8 +117,23 @@ def get_handle(device, D, C_total, C_local, class_offset, B, m, mode, rank=0, wo
     h = _HANDLES.get(key)
     if h is None:
         h = _Handle(device, D, C_total, C_local, class_offset, _round_batch(B), m, mode, rank, world)
+        h.key = key
         _HANDLES[key] = h
+        untagged = [k for k in _HANDLES if k[-1] is None]
+        for k in untagged[:max(0, len(untagged) - _MAX_HANDLES)]:
+            # stream-ordered frees: work already enqueued on the evicted handle still completes
+            _HANDLES.pop(k).close()
+    else:
+        _HANDLES.move_to_end(key)
     return h
+
+
+def drop_handle(h: Optional[_Handle]) -> None:
+    """Release a tagged handle together with the object that owned it."""
+    if h is None:
+        return
+    _HANDLES.pop(getattr(h, "key", None), None)
+    h.close()
 
 
 def release_handles() -> None:
@@ -176,7 +197,8 @@ def asoftmax_head(embeddings: torch.Tensor, labels: torch.Tensor, num_classes: i
                   lambda_state=None, *, weights: torch.Tensor, mode: str = "bf16",
                   return_logits: bool = False, compute_grads: bool = True,
                   check_labels: bool = False, optimizer: Optional["FusedOptimizer"] = None,
-                  _handle_tag=None
+                  grad_scale: float = 1.0, weight_decay: float = 0.0,
+                  reg_loss_out: Optional[torch.Tensor] = None, _handle_tag=None
                   ) -> Tuple[torch.Tensor, Optional[torch.Tensor], Optional[torch.Tensor], Optional[torch.Tensor]]:
     """A-softmax head forward + backward on one GPU that owns every class.
 
@@ -188,6 +210,11 @@ def asoftmax_head(embeddings: torch.Tensor, labels: torch.Tensor, num_classes: i
     [B, C] matrix to HBM), dX / dW are d(loss)/d(embeddings, weights).
     With `optimizer` (a FusedOptimizer) the classifier update is fused into the dW kernel:
     `weights` is updated IN PLACE and the returned dW is None.
+    `grad_scale`, `weight_decay`, `reg_loss_out` reproduce what the reference's towers do to the
+    gradients without a single extra pass over [D, C]: dX, dW come back multiplied by grad_scale
+    (mult_lr / num_gpus, data_parallel.py:37), dW includes weight_decay * W (the gradient of
+    reg_loss, nets/sphere.py:88) and reg_loss_out (a 1-element CUDA float tensor) receives
+    weight_decay/2 * |W|^2 (nets/net_base.py:103-107).  The returned loss is the plain cross-entropy.
     Asynchronous on the current CUDA stream.
     """
     _check_inputs(embeddings, labels, weights, num_classes)
@@ -203,7 +230,14 @@ def asoftmax_head(embeddings: torch.Tensor, labels: torch.Tensor, num_classes: i
     loss = torch.empty(1, device=X.device, dtype=torch.float32)
     logits = torch.empty(B, Cn, device=X.device, dtype=torch.float32) if return_logits else None
     stream = C.c_void_p(torch.cuda.current_stream(X.device).cuda_stream)
+    transform = grad_scale != 1.0 or weight_decay != 0.0 or reg_loss_out is not None
+    if reg_loss_out is not None and not (reg_loss_out.is_cuda and reg_loss_out.dtype == torch.float32
+                                         and reg_loss_out.numel() == 1):
+        raise TypeError("reg_loss_out must be a 1-element CUDA float32 tensor")
     with torch.cuda.device(X.device):
+        if transform:
+            _lib.check(h.lib.asm_set_gradient_transform(
+                h.ptr, grad_scale, weight_decay, reg_loss_out.data_ptr() if reg_loss_out is not None else None), h.ptr)
         if compute_grads:
             dX = torch.empty_like(X)
             dW = torch.empty_like(W) if optimizer is None else None
@@ -222,6 +256,8 @@ def asoftmax_head(embeddings: torch.Tensor, labels: torch.Tensor, num_classes: i
             rc = h.lib.asm_forward(
                 h.ptr, X.data_ptr(), B, y.data_ptr(), y.element_size(), W.data_ptr(), lam,
                 loss.data_ptr(), logits.data_ptr() if logits is not None else None, stream)
+        if transform:
+            h.lib.asm_set_gradient_transform(h.ptr, 1.0, 0.0, None)     # the handle is shared: back to defaults
         _lib.check(rc, h.ptr)
         if check_labels:
             _lib.check(h.lib.asm_check_labels(h.ptr, stream), h.ptr)
@@ -261,6 +297,7 @@ class GraphedASoftmaxStep:
         self.m, self.mode, self.Cn = m, mode, Cn
         self._tag = ("graph", id(self))
         h = get_handle(dev, D, Cn, Cn, 0, batch_size, m, mode, tag=self._tag)
+        self._key = h.key
         _lib.check(h.lib.asm_set_lambda_device(h.ptr, self.lam.data_ptr()), h.ptr)
         cur = torch.cuda.current_stream(dev)
         side = torch.cuda.Stream(dev)
@@ -279,6 +316,20 @@ class GraphedASoftmaxStep:
                                         mode=self.mode, _handle_tag=self._tag)
         return loss, dX, dW
 
+    def close(self):
+        """Drop the captured graph and this step's private handle (its device workspace)."""
+        self.graph = None
+        h = _HANDLES.get(getattr(self, "_key", None))
+        if h is not None:
+            drop_handle(h)
+        self._key = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
     def __call__(self, embeddings: torch.Tensor, labels: torch.Tensor, lambda_state=None):
         self._lam_host[0] = _as_lambda(lambda_state)
         self.lam.copy_(self._lam_host, non_blocking=True)
@@ -292,20 +343,26 @@ class GraphedASoftmaxStep:
 # torch autograd bridge: lets a torch backbone train through the fused head
 # --------------------------------------------------------------------------------------
 class ASoftmaxLoss(torch.autograd.Function):
-    """loss = ASoftmaxLoss.apply(embeddings, weights, labels, m, lam, mode).  The fused call
-    already produced dX and dW, so backward only scales them by the incoming gradient."""
+    """loss = ASoftmaxLoss.apply(embeddings, weights, labels, m, lam, mode[, upstream]).  The fused
+    call already produced dX and dW, so backward only hands them on.  `upstream` (a float) is the
+    gradient the caller promises to send into this loss (1.0 for a plain `loss.backward()`, the loss
+    scale otherwise): it is applied inside the kernels and backward returns the stored gradients
+    untouched -- no pass over [D, C].  Without it backward multiplies by the incoming gradient."""
 
     @staticmethod
-    def forward(ctx, embeddings, weights, labels, m, lam, mode):
-        loss, _, dX, dW = asoftmax_head(embeddings, labels, weights.shape[1], m, lam,
-                                        weights=weights, mode=mode)
+    def forward(ctx, embeddings, weights, labels, m, lam, mode, upstream=None):
+        loss, _, dX, dW = asoftmax_head(embeddings, labels, weights.shape[1], m, lam, weights=weights, mode=mode,
+                                        grad_scale=1.0 if upstream is None else float(upstream))
         ctx.save_for_backward(dX, dW)
+        ctx.upstream = upstream
         return loss
 
     @staticmethod
     def backward(ctx, grad_out):
         dX, dW = ctx.saved_tensors
-        return grad_out * dX, grad_out * dW, None, None, None, None
+        if ctx.upstream is not None:
+            return dX, dW, None, None, None, None, None
+        return grad_out * dX, grad_out * dW, None, None, None, None, None
 
 
 # --------------------------------------------------------------------------------------
@@ -325,7 +382,8 @@ class ASoftmaxHead:
 
     def __init__(self, num_features: int, num_classes: int, m: int = 4, weight_decay: float = 5e-4,
                  mode: str = "bf16", device="cuda", lambda_state: Optional[LambdaState] = None,
-                 return_logits: bool = False, seed: Optional[int] = None):
+                 return_logits: bool = False, seed: Optional[int] = None, num_gpus: int = 1,
+                 mult_lr: float = 1.0):
         gen = None
         if seed is not None:
             gen = torch.Generator(device="cpu").manual_seed(seed)
@@ -338,6 +396,10 @@ class ASoftmaxHead:
         self.mode = mode
         self.lambda_state = lambda_state if lambda_state is not None else LambdaState()
         self.return_logits = return_logits
+        # _grad_var scales every gradient by mult_lr * 1/num_gpus (data_parallel.py:37): known when
+        # the tower is built, so the kernels apply it and gradients() costs nothing
+        self.num_gpus, self.mult_lr = num_gpus, mult_lr
+        self._reg = torch.zeros(1, device=self.weights.device, dtype=torch.float32)
         self._last = None
 
     # nets/net_base.py:84-86, margin form data_parallel.py:220
@@ -347,10 +409,12 @@ class ASoftmaxHead:
         assert num_classes is not None, "num_classes must be given when is_training=True"
         assert labels is not None, "a margin head needs labels in forward (data_parallel.py:220)"
         lam = self.lambda_state.step()                # global_step += 1, first step uses it = 1
+        scale = self.mult_lr / self.num_gpus
         loss, logits, dX, dW = asoftmax_head(features, labels, num_classes, self.m, lam,
                                              weights=self.weights, mode=self.mode,
-                                             return_logits=self.return_logits)
-        self._last = dict(loss=loss, dX=dX, dW=dW, lam=lam)
+                                             return_logits=self.return_logits, grad_scale=scale,
+                                             weight_decay=self.weight_decay, reg_loss_out=self._reg)
+        self._last = dict(loss=loss, dX=dX, dW=dW, lam=lam, scale=scale, reg=self._reg[0].clone())
         out = {"logits": logits, "features": features}
         return out
 
@@ -359,23 +423,27 @@ class ASoftmaxHead:
         assert self._last is not None, "forward(...) must run first"
         losses = [self._last["loss"]]
         losses_name = ["cross_entropy"]
-        # _regularize (nets/net_base.py:103-107): contrib l2_regularizer = wd * sum(w^2)/2
-        reg = 0.5 * self.weight_decay * (self.weights * self.weights).sum()
-        losses.append(reg)
+        # _regularize (nets/net_base.py:103-107): contrib l2_regularizer = wd * sum(w^2)/2, a
+        # by-product of the norm kernel's column sums (no pass over W here)
+        losses.append(self._last["reg"])
         losses_name.append("reg_loss")
         others = OrderedDict()
         others["lambda"] = self._last["lam"]
         return losses, losses_name, others
 
-    def gradients(self, num_gpus: int = 1, mult_lr: float = 1.0):
-        """(dX, dW) of the cross-entropy term, scaled like _grad_var (data_parallel.py:37).
-        The L2 term's gradient wd * W is added to dW as tf.gradients(total_loss) would."""
-        s = mult_lr / num_gpus
-        dW = self._last["dW"] + self.weight_decay * self.weights
-        return self._last["dX"] * s, dW * s
+    def gradients(self, num_gpus: Optional[int] = None, mult_lr: Optional[float] = None):
+        """(dX, dW) of total_loss = cross_entropy + reg_loss, scaled like _grad_var
+        (data_parallel.py:37): both came out of the kernels in that form (dW includes wd * W).
+        Asking for a scale other than the configured one rescales them (one eager pass)."""
+        want = (self.mult_lr if mult_lr is None else mult_lr) / (self.num_gpus if num_gpus is None else num_gpus)
+        dX, dW = self._last["dX"], self._last["dW"]
+        if want != self._last["scale"]:
+            r = want / self._last["scale"]
+            return dX * r, dW * r
+        return dX, dW
 
     def param_list(self, is_training=True, trainable=True, scope=None):
         return [[self.weights]] if is_training else []
 
     def mult_lr_list(self, scope=None):
-        return [1.0]
+        return [self.mult_lr]

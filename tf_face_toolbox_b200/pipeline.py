@@ -18,7 +18,7 @@ import torch
 
 class HostPipelinedStep:
     def __init__(self, step_fn: Callable, batch: int, dim: int, device, labels_dtype=torch.int32,
-                 loss_stream: bool = False):
+                 loss_stream: bool = False, read_dx: bool = False):
         """loss_stream=True reads the loss back on a dedicated stream behind the step-end event
         instead of on the compute stream, so the 4-byte DMA no longer sits between two steps
         (opt-in until it has been measured on hardware)."""
@@ -27,6 +27,8 @@ class HostPipelinedStep:
         self.X = [torch.empty(batch, dim, device=self.dev, dtype=torch.float32) for _ in range(2)]
         self.y = [torch.empty(batch, device=self.dev, dtype=labels_dtype) for _ in range(2)]
         self.loss_host = [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(2)]
+        # read_dx: the step's dX (what a host-side consumer of the head gets back) is read D2H too
+        self.dx_host = [torch.zeros(batch, dim, dtype=torch.float32).pin_memory() for _ in range(2)] if read_dx else None
         self.copy_stream = torch.cuda.Stream(self.dev)
         self.d2h_stream = torch.cuda.Stream(self.dev) if loss_stream else None
         self.copied = [torch.cuda.Event() for _ in range(2)]
@@ -49,6 +51,8 @@ class HostPipelinedStep:
         self.out[i] = out
         self.consumed[i].record(cur)
         if self.d2h_stream is None:
+            if self.dx_host is not None:
+                self.dx_host[i].copy_(out[1], non_blocking=True)
             self.loss_host[i].copy_(out[0].reshape(1), non_blocking=True)
             self.loss_ready[i].record(cur)
         else:
@@ -56,6 +60,8 @@ class HostPipelinedStep:
             # been synchronised at step n+1, so the caching allocator cannot recycle it early
             with torch.cuda.stream(self.d2h_stream):
                 self.d2h_stream.wait_event(self.consumed[i])
+                if self.dx_host is not None:
+                    self.dx_host[i].copy_(out[1], non_blocking=True)
                 self.loss_host[i].copy_(out[0].reshape(1), non_blocking=True)
                 self.loss_ready[i].record(self.d2h_stream)
         prev = None

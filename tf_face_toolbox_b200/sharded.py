@@ -39,7 +39,9 @@ class _CudaShard:
     def __init__(self, D, C_total, lo, hi, m, mode, rank, world, device):
         self.args = (D, C_total, hi - lo, lo, m, mode, rank, world)
         self.device = torch.device(device)
-        self.tag = None
+        # a handle carries per-step state (the pointers of the step in flight, an armed optimizer):
+        # every shard object gets its own instead of sharing one with same-shaped callers
+        self.tag = ("shard", id(self))
         self.lambda_dev = None      # device scalar read by the kernels (CUDA-graph replay)
 
     def _handle(self, B):
@@ -87,7 +89,8 @@ class ShardedASoftmaxHead:
     def __init__(self, num_features: int, num_classes: int, m: int = 4, mode: str = "bf16",
                  device="cuda", group=None, lambda_state: Optional[LambdaState] = None,
                  weights_full: Optional[torch.Tensor] = None, seed: int = 0, shard_compute=None,
-                 transport: str = "nccl", batch_global: Optional[int] = None):
+                 transport: str = "nccl", batch_global: Optional[int] = None,
+                 weights_shard: Optional[torch.Tensor] = None):
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -96,7 +99,11 @@ class ShardedASoftmaxHead:
         if self.hi <= self.lo:
             raise ValueError("more ranks than classes: empty shard")
         self.device = torch.device(device)
-        if weights_full is not None:
+        if weights_shard is not None:              # this rank's [D, C_local] slice, e.g. scattered on the device
+            if tuple(weights_shard.shape) != (num_features, self.hi - self.lo):
+                raise ValueError(f"weights_shard must be [{num_features}, {self.hi - self.lo}]")
+            w = weights_shard.to(torch.float32)
+        elif weights_full is not None:
             w = weights_full[:, self.lo:self.hi].to(torch.float32)
         else:   # N(0, 0.001) like nets/sphere.py:87, generated shard-locally but rank-independent
             g = torch.Generator().manual_seed(seed)
@@ -179,16 +186,23 @@ class ShardedASoftmaxHead:
 
     # ---- one training step of the head -------------------------------------------------
     def step(self, embeddings_local: torch.Tensor, labels_local: torch.Tensor, lambda_state=None,
-             optimizer=None):
+             optimizer=None, center: Optional[dict] = None):
         """embeddings_local [B/G, D], labels_local [B/G] (this rank's data-parallel slice,
         data_parallel.py:206-207).  Returns (loss, dX_local [B/G, D], dW_local [D, C_local]);
         loss is the global-batch mean and identical on every rank.
         With `optimizer` (a FusedOptimizer owned by this rank) the shard's weights and optimizer
         state are updated in place inside the dW kernel and dW_local is None: this is the
         per-tower `apply_gradients` of data_parallel.py:186-196 without the G-fold redundancy --
-        each class column is updated exactly once, on the rank that owns it."""
+        each class column is updated exactly once, on the rank that owns it.
+        `center` = dict(centers=[C_local, D] shard, alpha=.., weight=..) adds the class-sharded
+        center loss (loss.py:29-45) on the same gathered batch: the shard's centers are updated in
+        place, its gradient joins the dX contribution before the reduce-scatter, and the returned
+        loss becomes (cross_entropy, center_loss summed over the shards).  Host-collective
+        transport only."""
         lam = _as_lambda(lambda_state) if lambda_state is not None else self.lambda_state.step()
         if self._p2p is not None:
+            if center is not None:
+                raise ValueError("the center loss runs with transport='nccl' (it needs the gathered batch on the host side)")
             return self._step_p2p(embeddings_local, labels_local, lam, optimizer=optimizer)
         b = embeddings_local.shape[0]
         X = self._all_gather(embeddings_local).reshape(-1, self.D)
@@ -199,6 +213,14 @@ class ShardedASoftmaxHead:
             loss, dX_partial, dW = self.compute.backward_partial(stats_all, X, self.weights, optimizer=optimizer)
         else:
             loss, dX_partial, dW = self.compute.backward_partial(stats_all, X, self.weights)
+        if center is not None:
+            from .center import center_loss
+            closs, _ = center_loss(X, y, center["centers"], center.get("alpha", 0.99), center.get("weight", 1.0),
+                                   class_offset=self.lo, grad_accum=dX_partial)
+            if self.world > 1:
+                closs = closs.clone()
+                dist.all_reduce(closs, group=self.group)
+            loss = (loss, closs)
         dX_local = self._reduce_scatter_rows(dX_partial, b)
         return loss, dX_local, dW
 

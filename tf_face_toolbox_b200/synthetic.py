@@ -20,6 +20,8 @@ CONFIGS = {
     "cfg3": dict(B=512, D=512, C=85742, mode="bf16"),
     "cfg4": dict(B=1024, D=512, C=1000000, mode="bf16"),
     "cfg5_head": dict(B=2048, D=512, C=85742, mode="bf16"),
+    # config 5 proper: the head plus the center loss (loss.py:29-45) on the same batch
+    "cfg5": dict(B=2048, D=512, C=85742, mode="bf16", center=True),
 }
 
 MIX = (1.5, 0.3, -0.3, -1.5)
