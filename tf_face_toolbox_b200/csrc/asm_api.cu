@@ -238,6 +238,7 @@ int run_forward(asm_head* h, const float* X, int B, const void* labels, int labe
       s.NT = umma_forward_tiles(B, s.Cp, h->num_sms, fcg, umma_tile_width(h->tune, ecg, funits, h->num_sms));
     }
     s.KS = umma_dx_splits(B, s.D, s.Cp, h->num_sms, (h->tune.cg_mask & 8) ? 2 : 1);
+    while (s.KS > 1 && (size_t)s.KS * B * s.D > h->dx_part_capacity) --s.KS;
     if (h->maps_B != B) {
       if (!umma_build_maps(&h->maps, s))
         return fail(h, ASM_ERR_CUDA, "cuTensorMapEncodeTiled failed%s", "");

@@ -200,6 +200,8 @@ struct UmmaMaps {            // TMA descriptors over the bf16 workspace operands
   // the caller's dW [D, C] fp32 seen as [D/2, 2C] (row pitch 8C bytes): even rows through a
   // tensor of extent {C, D/2}, odd rows through one of extent {2C, D/2} at column offset C
   CUtensorMap dw_even, dw_odd;
+  CUtensorMap dx_st;         // the dX split-K partials [KS][B][D] fp32 as a 3-D tensor (store, 128B swizzle)
+  int dx_ok;
   const void* dw_ptr;        // buffer the two maps above were encoded for (re-encoded when it changes)
   int dw_ok;                 // 0: dW cannot be addressed by TMA (odd C, misaligned base): direct stores
 };
@@ -224,6 +226,7 @@ struct UmmaArgs {
   int rev;                   // class tiles (or, with kstride, K blocks) in descending order
   int kstride;               // split-K: split z takes K blocks z, z + ks, ... instead of a contiguous range
   int dw_tma;                // DW: staged TMA stores (maps D / E valid)
+  int dx_tma;                // DX: staged TMA stores of the split-K partials (map C valid)
   int dw_shift;              // DW: class offset of the odd-row boxes (2 when C % 4 == 2, else 0)
   int store_evict_first;     // DW: the dW stores carry an evict-first L2 policy
 };

@@ -97,6 +97,15 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* s
       "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
       : "memory");
 }
+// 3-D variant (the dX split-K partials [KS][B][D]: rows past B are clipped per split)
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* smem_src, int32_t c0,
+                                             int32_t c1, int32_t c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+          reinterpret_cast<uint64_t>(m)),
+      "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
 // same, with an L2 cache-policy operand (e.g. kEvictFirst for data nothing reads again soon)
 __device__ __forceinline__ void tma_store_2d_hint(const CUtensorMap* m, const void* smem_src,
                                                   int32_t c0, int32_t c1, uint64_t policy) {

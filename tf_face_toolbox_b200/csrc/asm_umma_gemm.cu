@@ -177,7 +177,7 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
   if (warp == 0 && ptx::elect_one()) {
     ptx::prefetch_tmap(&mapA);
     ptx::prefetch_tmap(&mapB);
-    if (IS_BWDG || KIND == U_DW) ptx::prefetch_tmap(&mapC);
+    if (IS_BWDG || KIND == U_DW || KIND == U_DX) ptx::prefetch_tmap(&mapC);
     if (G_::DW_TMA) { ptx::prefetch_tmap(&mapD); ptx::prefetch_tmap(&mapE); }
   }
   if (warp == 1 && ptx::elect_one()) {
@@ -835,10 +835,34 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
         const int row = m0 + lane_row;
         const bool rv = row < s.B;
         float* out = s.dx_part + ((size_t)z * s.B + row) * s.D + n0 + col0;
+        // A thread owns a row, so a direct store instruction would write 32 separate 16-byte pieces
+        // 2 KB apart.  Instead the four warps of a column half stage [128 rows x 32 d] fp32 in the
+        // (otherwise unused) auxiliary region, 16-byte chunks XOR-swizzled by the row as
+        // CU_TENSOR_MAP_SWIZZLE_128B expects, and one TMA store writes the block; rows past B are
+        // clipped per split by the 3-D extent {D, B, KS}.
+        uint8_t* dstage = smem + PIPE_B + AUX_BARS + half * (128 * 128);
+        const bool leader = (threadIdx.x == 128 + half * 128);
         ptx::mbar_wait(&tfull[a], aph);
         ptx::tc_fence_after();
         auto process = [&](const uint32_t (&r)[32], int c) {
-          if (rv && n0 + col0 + c * 32 < s.D) {
+          if (g.dx_tma) {
+            float4* rowp = reinterpret_cast<float4*>(dstage + lane_row * 128);
+            const int sw = (ptx::smem_u32(rowp) >> 7) & 7;
+#pragma unroll
+            for (int qd = 0; qd < 8; ++qd)
+              rowp[qd ^ sw] = make_float4(__uint_as_float(r[4 * qd]), __uint_as_float(r[4 * qd + 1]),
+                                          __uint_as_float(r[4 * qd + 2]), __uint_as_float(r[4 * qd + 3]));
+            ptx::fence_proxy_async();
+            named_bar_sync(2 + half, 128);
+            if (leader) {
+              if (n0 + col0 + c * 32 < s.D) {
+                ptx::tma_store_3d(&mapC, dstage, n0 + col0 + c * 32, m0, z);
+                ptx::bulk_commit();
+              }
+              ptx::bulk_wait_read0();                          // the block is reused by the next chunk
+            }
+            named_bar_sync(2 + half, 128);
+          } else if (rv && n0 + col0 + c * 32 < s.D) {
 #pragma unroll
             for (int b = 0; b < 32; b += 4)
               *reinterpret_cast<float4*>(out + c * 32 + b) =
@@ -854,7 +878,7 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
       s.part[(size_t)fwd_row * s.NT + (pair_id / g.mt) * 2 + half] = make_float2(run_m, run_z);
   }
 
-  if ((IS_BWDG || G_::DW_TMA) && (threadIdx.x == 128 || threadIdx.x == 256)) ptx::bulk_wait0();
+  if ((IS_BWDG || G_::DW_TMA || KIND == U_DX) && (threadIdx.x == 128 || threadIdx.x == 256)) ptx::bulk_wait0();
   ptx::tc_fence_before();
   __syncthreads();
   if (CG == 2) ptx::cluster_sync_all();       // the peer may still be read / signalled by the leader
@@ -953,6 +977,19 @@ int umma_dx_splits(int B, int D, int Cp, int num_sms, int cg) {
   return (kb_total + kb_per - 1) / kb_per;       // every split non-empty
 }
 
+// fp32 [d2][d1][d0] tensor with 128-byte-swizzled boxes {32, 128, 1} (the dX partials)
+static bool encode_map3_f32(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint64_t d2) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {d0 * 4, d0 * d1 * 4};
+  cuuint32_t box[3] = {32, 128, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 bool umma_build_maps(UmmaMaps* m, const Step& s) {
   bool ok = true;
   // x3: the bf16 planes of each operand lie side by side along the inner dimension
@@ -971,6 +1008,8 @@ bool umma_build_maps(UmmaMaps* m, const Step& s) {
   ok &= encode_map(&m->g_mn, s.G, gi, s.Cp, gp, 64, 64);      // A of DX   (MN-major: M = batch, K = class)
   ok &= encode_map(&m->g_st, s.G, gi, s.Cp, gp, 32, 128, false, false, true);   // BWDG store (64B swizzle)
   ok &= encode_map(&m->wb_box, s.Wb, wc, s.D, wc, 128, 32, false); // DW weight chunks
+  // dX partials [KS][B][D] fp32 (D % 4 == 0, so every stride is a multiple of 16 bytes)
+  m->dx_ok = encode_map3_f32(&m->dx_st, s.dx_part, (uint64_t)s.D, (uint64_t)s.B, (uint64_t)(s.KS > 0 ? s.KS : 1)) ? 1 : 0;
   return ok;
 }
 
@@ -1184,8 +1223,9 @@ void launch_umma_dx(const Step& s, const UmmaMaps& m, const UmmaTuning& tu, int 
     g.rev = 1;
   }
   const int units = min(g.mt * g.nt * g.ks, num_sms / cg);
-  if (cg == 2) launch_k<U_DX, 2>(units, m.g_mn, m.wb_k128, m.wb_k128, s, g, st);
-  else launch_k<U_DX, 1>(units, m.g_mn, m.wb_k, m.wb_k, s, g, st);
+  g.dx_tma = (tu.dw_tma && m.dx_ok) ? 1 : 0;
+  if (cg == 2) launch_k<U_DX, 2>(units, m.g_mn, m.wb_k128, m.dx_st, s, g, st);
+  else launch_k<U_DX, 1>(units, m.g_mn, m.wb_k, m.dx_st, s, g, st);
 }
 
 }  // namespace asmh
