@@ -158,9 +158,14 @@ int asm_set_optimizer(asm_head* h, const asm_optimizer* opt, float* state0, floa
  *   dX_accum += weight * 2 (features - centers[labels]) / (B*D)       (optional, may be NULL)
  * A shard only touches rows whose label lies in [class_offset, class_offset + C_local); its
  * loss_out is that shard's partial sum / (B*D) (sum the shards' values).  `scratch` is a
- * caller-owned device buffer of (B + 1) floats whose last word is zero on first use.
- * Deterministic (no float atomics).  Stateless: no handle needed.
+ * caller-owned device buffer of asm_center_scratch_bytes(B) bytes (3 B + 4 words: row losses, the
+ * label-sorted row order, segment lengths, a ticket) that is ZERO on first use.  B <= 4096,
+ * D % 4 == 0.  Two launches: a one-block shared-memory sort of (label, row) that turns duplicate
+ * labels into contiguous segments, and one block per segment that reads its center row once, every
+ * member row once, and writes the center row once.  Deterministic (no float atomics; duplicates
+ * are summed in row order).  Stateless: no handle needed.
  */
+size_t asm_center_scratch_bytes(int32_t B);
 int asm_center_loss(const float* X, int32_t B, int32_t D, const void* labels, int32_t label_bytes,
                     float* centers, int32_t C_local, int32_t class_offset, float alpha,
                     float weight, float* loss_out, float* dX_accum_or_null, float* scratch,

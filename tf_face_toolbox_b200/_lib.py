@@ -66,6 +66,7 @@ SYMBOLS = {
     "asm_check_labels": (C.c_int, [_P, _P]),
     "asm_last_launch_count": (C.c_int, [_P]),
     "asm_set_optimizer": (C.c_int, [_P, C.POINTER(AsmOptimizer), _P, _P]),
+    "asm_center_scratch_bytes": (C.c_size_t, [C.c_int32]),
     "asm_center_loss": (C.c_int, [_P, C.c_int32, C.c_int32, _P, C.c_int32, _P, C.c_int32, C.c_int32,
                                   C.c_float, C.c_float, _P, _P, _P, _P]),
     "asm_p2p_bytes": (C.c_size_t, [C.POINTER(AsmConfig)]),

@@ -38,7 +38,7 @@ def center_loss(features: torch.Tensor, labels: torch.Tensor, centers: torch.Ten
     lib = _lib.load()
     grad = grad_accum if grad_accum is not None else torch.zeros_like(X)
     loss = torch.empty(1, device=X.device, dtype=torch.float32)
-    scratch = torch.zeros(B + 1, device=X.device, dtype=torch.float32)
+    scratch = torch.zeros(int(lib.asm_center_scratch_bytes(B)) // 4, device=X.device, dtype=torch.float32)
     stream = C.c_void_p(torch.cuda.current_stream(X.device).cuda_stream)
     with torch.cuda.device(X.device):
         rc = lib.asm_center_loss(X.data_ptr(), B, D, y.data_ptr(), y.element_size(), centers.data_ptr(),

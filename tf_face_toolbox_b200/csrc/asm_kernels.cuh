@@ -196,7 +196,7 @@ int simt_dx_splits(int B, int D, int Cp);
 
 // bf16 (tcgen05 / TMEM / TMA) contractions with fused epilogues
 struct UmmaMaps {            // TMA descriptors over the bf16 workspace operands
-  CUtensorMap xb_k, xb_k256, xb_mn, wb_mn, wb_mn32, wb_k, wb_k128, g_k, g_mn, g_st, wb_box;
+  CUtensorMap xb_k, xb_k256, xb_mn, wb_mn, wb_mn32, wb_k, wb_k128, g_k, g_mn, g_st, g_st32, wb_box;
   // the caller's dW [D, C] fp32 seen as [D/2, 2C] (row pitch 8C bytes): even rows through a
   // tensor of extent {C, D/2}, odd rows through one of extent {2C, D/2} at column offset C
   CUtensorMap dw_even, dw_odd;

@@ -128,6 +128,10 @@ __device__ __forceinline__ void bulk_commit() {
 __device__ __forceinline__ void bulk_wait_read0() {
   asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
+// all but the most recent committed bulk group of this thread have finished reading
+__device__ __forceinline__ void bulk_wait_read1() {
+  asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+}
 // ... have completed entirely (global writes performed)
 __device__ __forceinline__ void bulk_wait0() {
   asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");

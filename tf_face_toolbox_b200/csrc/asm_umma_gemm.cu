@@ -179,6 +179,7 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
     ptx::prefetch_tmap(&mapB);
     if (IS_BWDG || KIND == U_DW || KIND == U_DX) ptx::prefetch_tmap(&mapC);
     if (G_::DW_TMA) { ptx::prefetch_tmap(&mapD); ptx::prefetch_tmap(&mapE); }
+    if (IS_BWDG) ptx::prefetch_tmap(&mapD);
   }
   if (warp == 1 && ptx::elect_one()) {
     for (int i = 0; i < NST; ++i) {
@@ -625,31 +626,61 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
           // 16-byte chunks XOR-swizzled by the row (CU_TENSOR_MAP_SWIZZLE_64B) so that the eight
           // lanes of a store phase hit eight different bank groups.
           const int npl = s.x3 ? 2 : 1;
-          const int rsw = (lane_row >> 1) & 3;
 #pragma unroll 1
           for (int pl = 0; pl < npl; ++pl) {
-            uint8_t* sbuf = stg_half + (NSB == 2 ? ((c * npl + pl) & 1) * STG_HALF : 0);
-            uint4* rowp = reinterpret_cast<uint4*>(sbuf + lane_row * 64);
-            if (leader) ptx::bulk_wait_read0();               // earlier stores have drained their buffers
-            if (NSB == 1) named_bar_sync(2 + half, 128);
             uint32_t pk[16];
+            if (NSB == 2) {
+              // CTA pairs: every WARP owns two [32 classes x 32 batch] staging blocks and issues its
+              // own TMA store, so the eight epilogue warps never wait for each other: one
+              // __syncwarp per chunk instead of a 128-thread barrier.  Before block (c & 1) is
+              // rewritten, lane 0 confirms that the store before last has drained it.
+              uint8_t* sbuf = stg + ((warp - 4) * 2 + ((c * npl + pl) & 1)) * 2048;
+              uint4* rowp = reinterpret_cast<uint4*>(sbuf + lane * 64);
+              const int rsw = (lane >> 1) & 3;
+              if (lane == 0) ptx::bulk_wait_read1();
+              __syncwarp();
 #pragma unroll
-            for (int b = 0; b < 16; ++b) {
-              const __nv_bfloat162 hv = __floats2bfloat162_rn(gq[2 * b], gq[2 * b + 1]);
-              pk[b] = *reinterpret_cast<const uint32_t*>(&hv);
-              if (npl > 1) {
-                gq[2 * b] -= __low2float(hv);
-                gq[2 * b + 1] -= __high2float(hv);
+              for (int b = 0; b < 16; ++b) {
+                const __nv_bfloat162 hv = __floats2bfloat162_rn(gq[2 * b], gq[2 * b + 1]);
+                pk[b] = *reinterpret_cast<const uint32_t*>(&hv);
+                if (npl > 1) {
+                  gq[2 * b] -= __low2float(hv);
+                  gq[2 * b + 1] -= __high2float(hv);
+                }
               }
-            }
 #pragma unroll
-            for (int qd = 0; qd < 4; ++qd)
-              rowp[qd ^ rsw] = make_uint4(pk[4 * qd], pk[4 * qd + 1], pk[4 * qd + 2], pk[4 * qd + 3]);
-            ptx::fence_proxy_async();                         // generic writes -> async proxy
-            named_bar_sync(2 + half, 128);
-            if (leader && ib < s.Bp) {                        // chunks past the padded batch hold nothing
-              ptx::tma_store_2d(&mapC, sbuf, ib + pl * s.Bp, m0);
-              ptx::bulk_commit();
+              for (int qd = 0; qd < 4; ++qd)
+                rowp[qd ^ rsw] = make_uint4(pk[4 * qd], pk[4 * qd + 1], pk[4 * qd + 2], pk[4 * qd + 3]);
+              ptx::fence_proxy_async();                       // generic writes -> async proxy
+              __syncwarp();
+              if (lane == 0 && ib < s.Bp) {                   // chunks past the padded batch hold nothing
+                ptx::tma_store_2d(&mapD, sbuf, ib + pl * s.Bp, m0 + q4 * 32);
+                ptx::bulk_commit();
+              }
+            } else {
+              const int rsw = (lane_row >> 1) & 3;
+              uint8_t* sbuf = stg_half;
+              uint4* rowp = reinterpret_cast<uint4*>(sbuf + lane_row * 64);
+              if (leader) ptx::bulk_wait_read0();             // the earlier store has drained the block
+              named_bar_sync(2 + half, 128);
+#pragma unroll
+              for (int b = 0; b < 16; ++b) {
+                const __nv_bfloat162 hv = __floats2bfloat162_rn(gq[2 * b], gq[2 * b + 1]);
+                pk[b] = *reinterpret_cast<const uint32_t*>(&hv);
+                if (npl > 1) {
+                  gq[2 * b] -= __low2float(hv);
+                  gq[2 * b + 1] -= __high2float(hv);
+                }
+              }
+#pragma unroll
+              for (int qd = 0; qd < 4; ++qd)
+                rowp[qd ^ rsw] = make_uint4(pk[4 * qd], pk[4 * qd + 1], pk[4 * qd + 2], pk[4 * qd + 3]);
+              ptx::fence_proxy_async();
+              named_bar_sync(2 + half, 128);
+              if (leader && ib < s.Bp) {
+                ptx::tma_store_2d(&mapC, sbuf, ib + pl * s.Bp, m0);
+                ptx::bulk_commit();
+              }
             }
           }
         };
@@ -878,7 +909,7 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
       s.part[(size_t)fwd_row * s.NT + (pair_id / g.mt) * 2 + half] = make_float2(run_m, run_z);
   }
 
-  if ((IS_BWDG || G_::DW_TMA || KIND == U_DX) && (threadIdx.x == 128 || threadIdx.x == 256)) ptx::bulk_wait0();
+  if ((IS_BWDG || G_::DW_TMA || KIND == U_DX) && warp >= 4 && lane == 0) ptx::bulk_wait0();
   ptx::tc_fence_before();
   __syncthreads();
   if (CG == 2) ptx::cluster_sync_all();       // the peer may still be read / signalled by the leader
@@ -1007,6 +1038,7 @@ bool umma_build_maps(UmmaMaps* m, const Step& s) {
   ok &= encode_map(&m->g_k, s.G, gi, s.Cp, gp, 64, 128);      // A of DW   (K-major: K = batch, M = class)
   ok &= encode_map(&m->g_mn, s.G, gi, s.Cp, gp, 64, 64);      // A of DX   (MN-major: M = batch, K = class)
   ok &= encode_map(&m->g_st, s.G, gi, s.Cp, gp, 32, 128, false, false, true);   // BWDG store (64B swizzle)
+  ok &= encode_map(&m->g_st32, s.G, gi, s.Cp, gp, 32, 32, false, false, true);  // ... one warp's 32 classes
   ok &= encode_map(&m->wb_box, s.Wb, wc, s.D, wc, 128, 32, false); // DW weight chunks
   // dX partials [KS][B][D] fp32 (D % 4 == 0, so every stride is a multiple of 16 bytes)
   m->dx_ok = encode_map3_f32(&m->dx_st, s.dx_part, (uint64_t)s.D, (uint64_t)s.B, (uint64_t)(s.KS > 0 ? s.KS : 1)) ? 1 : 0;
@@ -1166,11 +1198,11 @@ void launch_umma_bwdg(const Step& s, const UmmaMaps& m, const UmmaTuning& tu, in
   set_segments(g, s.x3 != 0, (s.D + BK - 1) / BK, kSegLo, kSegHi, x3_segments(), s.Cp, s.D);
   g.rev = tu.l2_order ? 1 : 0;  // the forward kernel swept the classes upwards: start where it stopped
   const int units = min(g.mt * g.nt, num_sms / cg);
-  if (bn == 128) launch_k<U_BWDG, 2, 128>(units, m.wb_mn, m.xb_mn, m.g_st, s, g, st);   // X box: 64 rows per CTA
+  if (bn == 128) launch_k<U_BWDG, 2, 128>(units, m.wb_mn, m.xb_mn, m.g_st, s, g, st, &m.g_st32);   // X box: 64 rows per CTA
 #ifdef ASM_BRINGUP
   else if (cg == 2 && (tu.debug_flags & 8)) launch_k<U_BWDG1, 2>(units, m.wb_mn, m.xb_k, m.g_st, s, g, st);
 #endif
-  else if (cg == 2) launch_k<U_BWDG, 2>(units, m.wb_mn, m.xb_k, m.g_st, s, g, st);
+  else if (cg == 2) launch_k<U_BWDG, 2>(units, m.wb_mn, m.xb_k, m.g_st, s, g, st, &m.g_st32);
   else launch_k<U_BWDG, 1>(units, m.wb_mn, m.xb_k256, m.g_st, s, g, st);
 }
 

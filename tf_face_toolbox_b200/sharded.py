@@ -287,16 +287,20 @@ class ShardedASoftmaxHead:
         self._graph.replay()
         return self._gout
 
+    def gather_shard(self, shard: torch.Tensor) -> torch.Tensor:
+        """Any class-sharded [D, C_local] tensor (the weights, an optimizer slot) -> [D, C] on every rank."""
+        if self.world == 1:
+            return shard.clone()
+        per = -(-self.C // self.world)
+        pad = torch.zeros(self.D, per, device=shard.device, dtype=torch.float32)
+        pad[:, : self.hi - self.lo] = shard
+        allw = self._all_gather(pad)                                     # [G, D, per]
+        return allw.permute(1, 0, 2).reshape(self.D, -1)[:, : self.C].contiguous()
+
     def gather_weights(self) -> torch.Tensor:
         """All shards -> one [D, C] fp32 tensor (`classifier/fc_classifier/weights`, the
         layout saver.py:36-40 writes), for checkpoint compatibility."""
-        if self.world == 1:
-            return self.weights.clone()
-        per = -(-self.C // self.world)
-        pad = torch.zeros(self.D, per, device=self.weights.device, dtype=torch.float32)
-        pad[:, : self.hi - self.lo] = self.weights
-        allw = self._all_gather(pad)                                     # [G, D, per]
-        return allw.permute(1, 0, 2).reshape(self.D, -1)[:, : self.C].contiguous()
+        return self.gather_shard(self.weights)
 
     # ---- checkpoint layout (saver.py:30-80) ------------------------------------------------
     VARIABLE_NAME = "classifier/fc_classifier/weights"      # nets/sphere.py:84-90
