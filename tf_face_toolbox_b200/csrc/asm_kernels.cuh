@@ -212,6 +212,7 @@ struct UmmaTuning {          // MN-major shared-memory descriptor parameters (by
   uint32_t bn;               // tile width along N of FWD / BWDG / DW: 0 = chosen per launch from the unit count, 128, 256 (ASM_UMMA_BN)
   uint32_t l2_order;         // consecutive kernels sweep the classes in opposite directions (ASM_L2_ORDER=0 disables)
   uint32_t dw_tma;           // dW leaves through shared memory + TMA stores (ASM_DW_TMA=0: direct stores)
+  uint32_t side_by_side;     // per step: dW and dX run concurrently on disjoint SMs (ASM_DW_PAIRS)
   uint32_t l2_hints;         // evict-first on single-use streams: bit0 the fp32 W read of the norm kernel, bit1 the dW stores (ASM_L2_HINTS)
 };
 struct UmmaArgs {

@@ -433,6 +433,7 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
         pre0 = iv ? s.negoff[i] : -INFINITY;                  // -(lse_i log2e) + log2(1/B)
         pre1 = iv ? __int_as_float(s.ylocal[i]) : __int_as_float(-1);
         pre2 = iv ? s.gtarget[i] : 0.f;
+        pre3 = s.inv_c[pm * BM + lane_row];                    // 1/c of the class this thread owns next
       }
       if (IS_DW) {
         // raw loads only (no arithmetic here, so nothing waits on them until the next tile)
@@ -570,9 +571,9 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
         v0[et] = pre0;
         v1[et] = pre1;
         v2[et] = pre2;
+        const float ic = pre3;                                // fetched one tile ahead
         prefetch_tile(u + npairs);
         const int j = m0 + lane_row;                          // class (< Cp always)
-        const float ic = s.inv_c[j];
         const float icl = ic * LOG2E;
         // G'' leaves through shared memory: the four warps of a column half stage a
         // [32 rows x 128 classes] bf16 block and one thread issues a TMA store (rows >= B are
@@ -585,7 +586,7 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
         named_bar_sync(1, EPI_THREADS);
         ptx::mbar_wait(&tfull[a], aph);
         ptx::tc_fence_after();
-        float q0 = 0.f, q1 = 0.f;                             // sum_i G'_ij * acc_ij  (x ic later)
+        float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;         // sum_i G'_ij * acc_ij  (x ic later)
         const int jw0 = m0 + q4 * 32;                         // first class of this warp
         auto process = [&](const uint32_t (&r)[32], int c) {
           const int cb = col0 + c * 32;
@@ -599,25 +600,37 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
           const bool hit = __ballot_sync(0xffffffffu, static_cast<unsigned>(ylane - jw0) < 32u) != 0u;
           auto body = [&](auto patch_tag) {
             constexpr bool PATCH = decltype(patch_tag)::value;
+            // three passes over the chunk's 32 elements (exponent arguments, exponentials, products)
+            // instead of one fused pass: 32 independent MUFU operations issue back to back
 #pragma unroll
             for (int b4 = 0; b4 < 8; ++b4) {
               const float4 no = *reinterpret_cast<const float4*>(v0 + cb + b4 * 4);
-              const float nof[4] = {no.x, no.y, no.z, no.w};
-              int yv[4] = {0, 0, 0, 0};
-              if (PATCH) {
-                const int4 yy = *reinterpret_cast<const int4*>(v1 + cb + b4 * 4);
-                yv[0] = yy.x; yv[1] = yy.y; yv[2] = yy.z; yv[3] = yy.w;
-              }
+              gq[b4 * 4 + 0] = fmaf(__uint_as_float(r[b4 * 4 + 0]), icl, no.x);
+              gq[b4 * 4 + 1] = fmaf(__uint_as_float(r[b4 * 4 + 1]), icl, no.y);
+              gq[b4 * 4 + 2] = fmaf(__uint_as_float(r[b4 * 4 + 2]), icl, no.z);
+              gq[b4 * 4 + 3] = fmaf(__uint_as_float(r[b4 * 4 + 3]), icl, no.w);
+            }
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const int b = b4 * 4 + e;
-                const float acc = __uint_as_float(r[b]);
-                float gp = fast_ex2(fmaf(acc, icl, nof[e]));    // softmax prob / B
-                if (PATCH && yv[e] == j) gp = v2[cb + b];       // target column: G'_{i,y}
-                if (e & 1) q1 = fmaf(gp, acc, q1); else q0 = fmaf(gp, acc, q0);
-                gq[b] = gp * ic;
+            for (int b = 0; b < 32; ++b) gq[b] = fast_ex2(gq[b]);    // softmax prob / B
+            if (PATCH) {
+#pragma unroll
+              for (int b4 = 0; b4 < 8; ++b4) {
+                const int4 yy = *reinterpret_cast<const int4*>(v1 + cb + b4 * 4);
+                if (yy.x == j) gq[b4 * 4 + 0] = v2[cb + b4 * 4 + 0];   // target column: G'_{i,y}
+                if (yy.y == j) gq[b4 * 4 + 1] = v2[cb + b4 * 4 + 1];
+                if (yy.z == j) gq[b4 * 4 + 2] = v2[cb + b4 * 4 + 2];
+                if (yy.w == j) gq[b4 * 4 + 3] = v2[cb + b4 * 4 + 3];
               }
             }
+#pragma unroll
+            for (int b = 0; b < 32; b += 4) {
+              q0 = fmaf(gq[b + 0], __uint_as_float(r[b + 0]), q0);
+              q1 = fmaf(gq[b + 1], __uint_as_float(r[b + 1]), q1);
+              q2 = fmaf(gq[b + 2], __uint_as_float(r[b + 2]), q2);
+              q3 = fmaf(gq[b + 3], __uint_as_float(r[b + 3]), q3);
+            }
+#pragma unroll
+            for (int b = 0; b < 32; ++b) gq[b] *= ic;
           };
           if (hit) body(std::true_type{}); else body(std::false_type{});
           // x3: G'' leaves as two bf16 planes (value, then the rounding residual), side by side
@@ -685,7 +698,7 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
           }
         };
         ASM_EPILOGUE_CHUNKS(process)
-        s.q_part[(size_t)(n_idx * 2 + half) * s.Cp + j] = (q0 + q1) * ic;
+        s.q_part[(size_t)(n_idx * 2 + half) * s.Cp + j] = ((q0 + q1) + (q2 + q3)) * ic;
       } else if (KIND == U_DW) {
         // ---- thread = class j, columns = d.  dW[d][j] = acc - Wb[d][j] * q_j / c_j^2
         // The q_j partials and 1/c_j were fetched one tile ahead; the bf16 weight chunks
@@ -1250,9 +1263,9 @@ void launch_umma_dx(const Step& s, const UmmaMaps& m, const UmmaTuning& tu, int 
                s.Bp, s.Cp);
   g.ks = s.KS;
   g.kb_per = (g.kb_total + g.ks - 1) / g.ks;
-  if (tu.l2_order && !s.x3) {   // all splits sweep the classes together, downwards (DW went up)
-    g.kstride = 1;
-    g.rev = 1;
+  if (tu.l2_order && !s.x3) {   // all splits sweep the classes together, downwards (DW went up) --
+    g.kstride = 1;              // or upwards WITH it when the two kernels share the SMs (num_sms < all)
+    g.rev = tu.side_by_side ? 0 : 1;
   }
   const int units = min(g.mt * g.nt * g.ks, num_sms / cg);
   g.dx_tma = (tu.dw_tma && m.dx_ok) ? 1 : 0;
