@@ -624,19 +624,23 @@ def run_ours(args, cfg):
         if name in wl.host_paths or wl.center is not None:
             continue                          # graph steps own their static input buffers
         src = wl.head_nv if name == "nvlink" else (wl.head if world > 1 else None)
-        if src is not None:
-            runner = HostPipelinedStep(lambda X, y, _h=src: _h.step(X, y, LAMBDA), b_local, D, dev, read_dx=True)
-        else:
-            runner = HostPipelinedStep(lambda X, y: (lambda o: (o[0], o[2], o[3]))(
-                asoftmax_head(X, y, Cn, M_MARGIN, LAMBDA, weights=wl.Wd, mode=mode)), b_local, D, dev, read_dx=True)
+        # results read back on the compute stream (between two steps) or on a stream of their own
+        for suffix, own_stream in (("_pipelined", False), ("_pipelined_d2h_stream", True)):
+            if src is not None:
+                runner = HostPipelinedStep(lambda X, y, _h=src: _h.step(X, y, LAMBDA), b_local, D, dev,
+                                           read_dx=True, loss_stream=own_stream)
+            else:
+                runner = HostPipelinedStep(lambda X, y: (lambda o: (o[0], o[2], o[3]))(
+                    asoftmax_head(X, y, Cn, M_MARGIN, LAMBDA, weights=wl.Wd, mode=mode)), b_local, D, dev,
+                    read_dx=True, loss_stream=own_stream)
 
-        def fn(_r=runner):
-            return _r.submit(Xh, yh)
-        for _ in range(3):
-            fn()
-        runner.flush()
-        e2e_ms[name + "_pipelined"] = wl.timed(lambda: (fn()), K) / K - flush_ms
-        runner.flush()
+            def fn(_r=runner):
+                return _r.submit(Xh, yh)
+            for _ in range(3):
+                fn()
+            runner.flush()
+            e2e_ms[name + suffix] = wl.timed(lambda: (fn()), K) / K - flush_ms
+            runner.flush()
     # ... and through the reference-shaped drop-in surface: forward / loss_function / gradients of
     # the Network-shaped wrapper (nets/net_base.py:84-107, data_parallel.py:220-236)
     if world == 1 and wl.center is None:
