@@ -217,6 +217,14 @@ int asm_p2p_status(asm_head* h, void* cuda_stream);
  */
 int asm_set_gradient_transform(asm_head* h, float grad_scale, float weight_decay, float* reg_loss_out);
 
+/*
+ * Element type of the embeddings handed to the step calls: 4 = fp32 (default, what the reference's
+ * backbones emit), 2 = bf16 (ASM_MODE_BF16 only).  With 2, every X / X_local pointer is a bf16
+ * [B, D] array: the norm kernel skips the rounding it would do itself, the r_i x_i term of dX reads
+ * the bf16 rows, and the NVLink transport publishes and gathers half the bytes.  dX stays fp32.
+ */
+int asm_set_embedding_dtype(asm_head* h, int32_t bytes_per_element);
+
 /* CUDA-graph support.  Kernel arguments are frozen when a step is captured into a graph, so
  * lambda (which anneals per step) can instead be read from a caller-owned DEVICE float:
  * once set (non-NULL) it overrides the by-value `lambda` argument of every step call; NULL

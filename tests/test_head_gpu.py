@@ -570,3 +570,25 @@ def test_bf16_cfg4_shard_geometry_vs_streamed_oracle():
     for (lo, hi), want in r.dW.items():
         base = 0 if lo < 125000 else 125000
         assert cosine(dWs[base][:, lo - base:hi - base].cpu().numpy(), want) >= 0.9999, (lo, hi)
+
+
+def test_bf16_embeddings_at_the_boundary():
+    """asm_set_embedding_dtype: embeddings handed over as bf16 (bf16 mode) give the same result as the
+    same values handed over as fp32 (the library would round them to bf16 itself)."""
+    dev = torch.device("cuda:0")
+    inp = make_inputs(300, 192, 2002, seed=61)
+    X16 = inp.X.to(dev).to(torch.bfloat16)
+    X32 = X16.float()
+    y, W = inp.y.to(dev), inp.W.to(dev)
+    la, _, dXa, dWa = asoftmax_head(X32, y, 2002, 4, 5.0, weights=W, mode="bf16")
+    lb, _, dXb, dWb = asoftmax_head(X16, y, 2002, 4, 5.0, weights=W, mode="bf16")
+    torch.cuda.synchronize()
+    assert dXb.dtype == torch.float32
+    # same operand bits; only the summation order inside the row norms differs (8 vs 4 elements per lane)
+    assert float(la) == pytest.approx(float(lb), rel=1e-6)
+    torch.testing.assert_close(dXa, dXb, rtol=1e-4, atol=1e-7 * float(dXa.abs().max()) + 1e-12)
+    torch.testing.assert_close(dWa, dWb, rtol=1e-4, atol=1e-5 * float(dWa.abs().max()) + 1e-12)
+    r = ref.asoftmax_head(X32.cpu().numpy(), inp.W.numpy(), inp.y.numpy(), 4, 5.0)
+    assert abs(float(lb) - r.loss) <= 2e-3 * r.loss and cosine(dXb.cpu().numpy(), r.dX) >= 0.9999
+    with pytest.raises(TypeError):
+        asoftmax_head(X16, y, 2002, 4, 5.0, weights=W, mode="fp32")

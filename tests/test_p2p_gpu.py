@@ -209,3 +209,22 @@ def test_p2p_step_with_fused_optimizer(mode):
         assert cosine(upd, want) >= 0.9999, g
         np.testing.assert_allclose(upd, want, rtol=0, atol=(2e-3 if mode == "fp32" else 3e-2) * np.abs(want).max())
     ranks.dW = saved_dW
+
+
+def test_p2p_step_with_bf16_embeddings():
+    """The transport publishes and gathers bf16 rows when the embeddings are handed over as bf16."""
+    G, B, D, Cn = 4, 128, 128, 5000
+    inp = make_inputs(B, D, Cn, seed=80)
+    inp = type(inp)(inp.X.to(torch.bfloat16).float(), inp.W, inp.y)      # values exactly representable in bf16
+    ranks = FakeRanks(inp, G, "bf16", "p2p-x16")
+    ranks.step(5.0)
+    r = ref.asoftmax_head(inp.X.numpy(), inp.W.numpy(), inp.y.numpy(), 4, 5.0)
+    ranks.check(r)
+    want = [t.clone() for t in ranks.dX]
+    for g, h in enumerate(ranks.handles):
+        _lib.check(h.lib.asm_set_embedding_dtype(h.ptr, 2), h.ptr)
+        ranks.X[g] = ranks.X[g].to(torch.bfloat16)
+    ranks.step(5.0)
+    ranks.check(r)
+    for a, b in zip(want, ranks.dX):      # same operand bits, row norms summed in a different order
+        torch.testing.assert_close(a, b, rtol=1e-4, atol=1e-7 * float(a.abs().max()) + 1e-12)

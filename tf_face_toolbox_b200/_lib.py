@@ -75,6 +75,7 @@ SYMBOLS = {
     "asm_p2p_set_timeout": (C.c_int, [_P, C.c_int32]),
     "asm_p2p_status": (C.c_int, [_P, _P]),
     "asm_set_gradient_transform": (C.c_int, [_P, C.c_float, C.c_float, _P]),
+    "asm_set_embedding_dtype": (C.c_int, [_P, C.c_int32]),
     "asm_set_lambda_device": (C.c_int, [_P, _P]),
     "asm_set_profiling": (C.c_int, [_P, C.c_int]),
     "asm_get_profile": (C.c_int, [_P, C.c_int32, _P, _P]),

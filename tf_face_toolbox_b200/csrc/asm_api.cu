@@ -699,6 +699,16 @@ int asm_set_gradient_transform(asm_head* h, float grad_scale, float weight_decay
   return ASM_OK;
 }
 
+int asm_set_embedding_dtype(asm_head* h, int32_t bytes_per_element) {
+  if (!h) return ASM_ERR_INVALID_ARG;
+  if (bytes_per_element != 4 && bytes_per_element != 2)
+    return fail(h, ASM_ERR_INVALID_ARG, "embedding elements are 4 (fp32) or 2 (bf16) bytes%s", "");
+  if (bytes_per_element == 2 && h->cfg.mode != ASM_MODE_BF16)
+    return fail(h, ASM_ERR_INVALID_ARG, "bf16 embeddings need ASM_MODE_BF16%s", "");
+  h->st.x_bf16 = bytes_per_element == 2 ? 1 : 0;
+  return ASM_OK;
+}
+
 int asm_set_lambda_device(asm_head* h, const float* lambda_dev) {
   if (!h) return ASM_ERR_INVALID_ARG;
   h->st.lambda_dev = lambda_dev;

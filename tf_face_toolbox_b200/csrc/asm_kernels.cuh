@@ -117,7 +117,8 @@ struct Step {
   float* wsq_part;           // [W-role blocks of the norm kernel] partial sums of w^2
   unsigned int* wsq_ticket;  // [1]
   // caller buffers (device)
-  const float* X;            // [B, D]
+  const float* X;            // [B, D] fp32, or bf16 when x_bf16 (bf16 mode only)
+  int x_bf16;
   const float* W;            // [D, C]
   float* logits;             // [B, C] or null
   float* dX;                 // [B, D]

@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(256) prep_kernel(Step s, const void* labels, i
     const unsigned cur = p2p_current_step(p);
     float4* xs = reinterpret_cast<float4*>(p.x(p.rank, cur & 1));
     int* ys = p.y(p.rank, cur & 1);
-    const size_t n4 = (size_t)p.b_local * p.D / 4;
+    const size_t n4 = (size_t)p.b_local * p.D * (s.x_bf16 ? 2 : 4) / 16;     // 16-byte pieces of my rows
     for (size_t i = blockIdx.x * (size_t)256 + tid; i < n4; i += (size_t)npub * 256)
       xs[i] = __ldg(reinterpret_cast<const float4*>(p.x_local) + i);
     for (int i = blockIdx.x * 256 + tid; i < p.b_local; i += npub * 256)
@@ -138,8 +138,10 @@ __global__ void __launch_bounds__(256) prep_kernel(Step s, const void* labels, i
     const int tx = tid & 31;
     const int row = (bid - nwb) * 8 + (tid >> 5);
     if (row >= s.B) return;
-    const float* x = s.X + (size_t)row * s.D;
-    float* xg = nullptr;
+    // embeddings arrive as fp32 or (bf16 mode, asm_set_embedding_dtype) as bf16: `esz` bytes each
+    const int esz = s.x_bf16 ? 2 : 4;
+    const char* x = reinterpret_cast<const char*>(s.X) + (size_t)row * s.D * esz;
+    char* xg = nullptr;
     long long y;
     if (npub > 0) {
       // gathered batch: row `row` lives in the symmetric block of rank row / b_local
@@ -147,16 +149,15 @@ __global__ void __launch_bounds__(256) prep_kernel(Step s, const void* labels, i
       const int src = row / p.b_local, lr = row - src * p.b_local;
       if (tx == 0) p2p_wait(p, 0, src, cur);
       __syncwarp();
-      x = p.x(src, cur & 1) + (size_t)lr * s.D;
-      xg = p.Xg + (size_t)row * s.D;             // fp32 copy for the r_i x_i term of dX
+      x = reinterpret_cast<const char*>(p.x(src, cur & 1)) + (size_t)lr * s.D * esz;
+      xg = reinterpret_cast<char*>(p.Xg) + (size_t)row * s.D * esz;   // copy for the r_i x_i term of dX
       y = (long long)__ldcv(p.y(src, cur & 1) + lr);
     } else {
       y = label_bytes == 8 ? reinterpret_cast<const long long*>(labels)[row]
                            : (long long)reinterpret_cast<const int*>(labels)[row];
     }
     float acc = 0.f;
-    auto emit = [&](int d, float v) {               // one element: norm, gathered copy, bf16 planes
-      if (npub > 0) xg[d] = v;
+    auto emit = [&](int d, float v) {               // one element: norm, bf16 planes
       acc = fmaf(v, v, acc);
       if (PL > 0) {
         __nv_bfloat16* dst = s.Xb + (size_t)row * PL * s.D + d;
@@ -169,28 +170,40 @@ __global__ void __launch_bounds__(256) prep_kernel(Step s, const void* labels, i
         }
       }
     };
-    if (npub > 0) {
-      // a peer's row: every load is an NVLink round trip, so up to 4 x 16 bytes per lane (a row
-      // of D <= 512) are requested back to back before the first value is used
+    auto emit16 = [&](int e0, const float4& v) {    // one 16-byte piece: 4 fp32 or 8 bf16 elements
+      if (s.x_bf16) {
+        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          emit(e0 + 2 * q, __low2float(h2[q]));
+          emit(e0 + 2 * q + 1, __high2float(h2[q]));
+        }
+      } else {
+        emit(e0, v.x); emit(e0 + 1, v.y); emit(e0 + 2, v.z); emit(e0 + 3, v.w);
+      }
+    };
+    {
+      // 16-byte pieces of the row, up to 4 per lane requested back to back (for a peer's row every
+      // load is an NVLink round trip: nothing is used before all of them are in flight)
       const float4* x4 = reinterpret_cast<const float4*>(x);
-      const int n4 = s.D / 4;                        // D % 16 == 0
-      for (int i0 = 0; i0 < n4; i0 += 128) {
+      const int n16 = s.D * esz / 16;                // D % 16 == 0
+      const int epp = 16 / esz;                      // elements per piece
+      for (int i0 = 0; i0 < n16; i0 += 128) {
         float4 v[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const int i = i0 + u * 32 + tx;
-          v[u] = i < n4 ? __ldcv(x4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+          v[u] = i < n16 ? (npub > 0 ? __ldcv(x4 + i) : __ldg(x4 + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const int i = i0 + u * 32 + tx;
-          if (i < n4) {
-            emit(4 * i, v[u].x); emit(4 * i + 1, v[u].y); emit(4 * i + 2, v[u].z); emit(4 * i + 3, v[u].w);
+          if (i < n16) {
+            if (npub > 0) reinterpret_cast<float4*>(xg)[i] = v[u];
+            emit16(i * epp, v[u]);
           }
         }
       }
-    } else {
-      for (int d = tx; d < s.D; d += 32) emit(d, __ldg(x + d));
     }
     acc = warp_sum(acc);
     if (tx == 0) {

@@ -49,7 +49,15 @@ __device__ __forceinline__ void dx_finish_rows(const Step& s, float* dxo, unsign
     const int row = (int)((i * 4) / s.D);
     const float4* p = reinterpret_cast<const float4*>(s.dx_part) + i;
     const float r = s.rcoef[row];
-    const float4 x = __ldg(reinterpret_cast<const float4*>(s.X) + i);
+    float4 x;
+    if (s.x_bf16) {                                   // embeddings handed over as bf16
+      const uint2 h = __ldg(reinterpret_cast<const uint2*>(s.X) + i);
+      const __nv_bfloat162 a2 = *reinterpret_cast<const __nv_bfloat162*>(&h.x);
+      const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&h.y);
+      x = make_float4(__low2float(a2), __high2float(a2), __low2float(b2), __high2float(b2));
+    } else {
+      x = __ldg(reinterpret_cast<const float4*>(s.X) + i);
+    }
     float4 a = make_float4(r * x.x, r * x.y, r * x.z, r * x.w);
     if (KS_T > 0) {
       float4 v[KS_T > 0 ? KS_T : 1];

@@ -181,8 +181,10 @@ class FusedOptimizer:
 def _check_inputs(embeddings, labels, weights, num_classes):
     if not (embeddings.is_cuda and labels.is_cuda and weights.is_cuda):
         raise RuntimeError("embeddings, labels and weights must be CUDA tensors (no CPU fallback)")
-    if embeddings.dtype != torch.float32 or weights.dtype != torch.float32:
-        raise TypeError("embeddings and weights must be float32 (bf16 rounding happens inside the library)")
+    if weights.dtype != torch.float32:
+        raise TypeError("weights must be float32 (the master copy; bf16 rounding happens inside the library)")
+    if embeddings.dtype not in (torch.float32, torch.bfloat16):
+        raise TypeError("embeddings must be float32, or bfloat16 in bf16 mode")
     if labels.dtype not in (torch.int32, torch.int64):
         raise TypeError("labels must be int32 (reference dtype, data.py:259) or int64")
     if embeddings.dim() != 2 or weights.dim() != 2 or labels.dim() != 1:
@@ -218,6 +220,8 @@ def asoftmax_head(embeddings: torch.Tensor, labels: torch.Tensor, num_classes: i
     Asynchronous on the current CUDA stream.
     """
     _check_inputs(embeddings, labels, weights, num_classes)
+    if embeddings.dtype == torch.bfloat16 and mode != "bf16":
+        raise TypeError("bfloat16 embeddings need mode='bf16'")
     X = embeddings.contiguous()
     if optimizer is not None and not weights.is_contiguous():
         raise ValueError("a fused optimizer updates `weights` in place: it must be contiguous")
@@ -234,12 +238,15 @@ def asoftmax_head(embeddings: torch.Tensor, labels: torch.Tensor, num_classes: i
     if reg_loss_out is not None and not (reg_loss_out.is_cuda and reg_loss_out.dtype == torch.float32
                                          and reg_loss_out.numel() == 1):
         raise TypeError("reg_loss_out must be a 1-element CUDA float32 tensor")
+    x16 = X.dtype == torch.bfloat16
     with torch.cuda.device(X.device):
+        if x16:
+            _lib.check(h.lib.asm_set_embedding_dtype(h.ptr, 2), h.ptr)
         if transform:
             _lib.check(h.lib.asm_set_gradient_transform(
                 h.ptr, grad_scale, weight_decay, reg_loss_out.data_ptr() if reg_loss_out is not None else None), h.ptr)
         if compute_grads:
-            dX = torch.empty_like(X)
+            dX = torch.empty(X.shape, device=X.device, dtype=torch.float32)
             dW = torch.empty_like(W) if optimizer is None else None
             if optimizer is not None:
                 optimizer._arm(h, W)
@@ -258,6 +265,8 @@ def asoftmax_head(embeddings: torch.Tensor, labels: torch.Tensor, num_classes: i
                 loss.data_ptr(), logits.data_ptr() if logits is not None else None, stream)
         if transform:
             h.lib.asm_set_gradient_transform(h.ptr, 1.0, 0.0, None)     # the handle is shared: back to defaults
+        if x16:
+            h.lib.asm_set_embedding_dtype(h.ptr, 4)
         _lib.check(rc, h.ptr)
         if check_labels:
             _lib.check(h.lib.asm_check_labels(h.ptr, stream), h.ptr)

@@ -54,6 +54,7 @@ class _CudaShard:
     def forward_partial(self, X, y, W, lam):
         B = X.shape[0]
         h = self._handle(B)
+        _lib.check(h.lib.asm_set_embedding_dtype(h.ptr, X.element_size()), h.ptr)    # fp32, or bf16 in bf16 mode
         stats = torch.empty(3, B, device=X.device, dtype=torch.float32)
         stream = C.c_void_p(torch.cuda.current_stream(X.device).cuda_stream)
         with torch.cuda.device(X.device):
@@ -66,7 +67,7 @@ class _CudaShard:
         B = X.shape[0]
         h = self._handle(B)
         loss = torch.empty(1, device=X.device, dtype=torch.float32)
-        dXp = torch.empty_like(X)
+        dXp = torch.empty(X.shape, device=X.device, dtype=torch.float32)
         dW = torch.empty_like(W) if optimizer is None else None     # fused update: dW never exists
         stream = C.c_void_p(torch.cuda.current_stream(X.device).cuda_stream)
         with torch.cuda.device(X.device):
@@ -168,10 +169,11 @@ class ShardedASoftmaxHead:
         y = labels_local.contiguous()
         b = X.shape[0]
         loss = torch.empty(1, device=X.device, dtype=torch.float32)
-        dX = torch.empty_like(X)
+        dX = torch.empty(X.shape, device=X.device, dtype=torch.float32)
         dW = torch.empty_like(self.weights) if optimizer is None else None
         stream = C.c_void_p(torch.cuda.current_stream(X.device).cuda_stream)
         with torch.cuda.device(X.device):
+            _lib.check(h.lib.asm_set_embedding_dtype(h.ptr, X.element_size()), h.ptr)   # bf16 rows: half the NVLink bytes
             if optimizer is not None:
                 optimizer._arm(h, self.weights)
             try:
