@@ -576,7 +576,21 @@ def run_ours(args, cfg):
             kernels.setdefault(nm, []).append(ms_buf[i])
     h.lib.asm_set_profiling(h.ptr, 0)
     kavg = {k: sum(v) / len(v) for k, v in kernels.items()}
-    note("profile loop done")
+    # the same with events only between PHASES, which leaves the real schedule in place (the dW
+    # kernel next to the dX branch on disjoint CTA pairs counts as one phase)
+    phases = {}
+    h.lib.asm_set_profiling(h.ptr, 2)
+    for _ in range(K):
+        if wl.flush is not None:
+            wl.flush.zero_()
+        prof_step()
+        n = h.lib.asm_get_profile(h.ptr, 16, ms_buf, names)
+        for i in range(max(n, 0)):
+            nm = names.raw[i * 32:(i + 1) * 32].split(b"\0")[0].decode()
+            phases.setdefault(nm, []).append(ms_buf[i])
+    h.lib.asm_set_profiling(h.ptr, 0)
+    pavg = {k: sum(v) / len(v) for k, v in phases.items()}
+    note("profile loops done")
 
     # ---- (3) end to end with HOST buffers: H2D of the step's inputs and D2H of its results (the
     # loss AND dX, the gradient the backbone consumes) inside the timed region, every step
@@ -682,7 +696,7 @@ def run_ours(args, cfg):
 
     line = None
     if rank == 0:
-        line = build_line(args, cfg, world, mode, peaks, kavg, value, ms_step, value_path, value_ms, step_dist,
+        line = build_line(args, cfg, world, mode, peaks, kavg, pavg, value, ms_step, value_path, value_ms, step_dist,
                           e2e_value, ms_e2e, e2e_path, e2e_ms, b_local, launches_per_step, K, Wm, clocks, parity,
                           knobs, bringup, _lib.load().asm_version().decode(), "graph" in wl.paths or "nvlink_graph" in wl.paths)
     wl.close()
@@ -728,7 +742,7 @@ def run_ours(args, cfg):
         bail.cancel()
 
 
-def build_line(args, cfg, world, mode, peaks, kavg, value, ms_step, value_path, value_ms, step_dist, e2e_value,
+def build_line(args, cfg, world, mode, peaks, kavg, pavg, value, ms_step, value_path, value_ms, step_dist, e2e_value,
                ms_e2e, e2e_path, e2e_ms, b_local, launches_per_step, K, Wm, clocks, parity, knobs, bringup, version,
                has_graph):
     B, D, Cn = cfg["B"], cfg["D"], cfg["C"]
@@ -760,6 +774,17 @@ def build_line(args, cfg, world, mode, peaks, kavg, value, ms_step, value_path, 
                                  "frac": ach / peaks["hbm"], "algorithmic_bytes": by})
         else:
             roof_kernels.append({"kernel": nm, "ms": ms})
+    # phases as they really run (events only where the main stream serialises anyway)
+    phase_list = []
+    for nm, ms in pavg.items():
+        rec = {"phase": nm, "ms": ms}
+        if nm.startswith("dw+dx"):
+            # two contractions (4 B D C flop) and the one fp32 write of dW (4 D C bytes), side by side
+            rec.update({"algorithmic_flops": 2 * gemm_flops, "tensor_tflops": 2 * gemm_flops / (ms * 1e-3) / 1e12,
+                        "tensor_frac": 2 * gemm_flops / (ms * 1e-3) / 1e12 / peaks["tf_burst"],
+                        "algorithmic_bytes": 4.0 * D * C_local, "hbm_gbs": 4.0 * D * C_local / (ms * 1e-3) / 1e9,
+                        "hbm_frac": 4.0 * D * C_local / (ms * 1e-3) / 1e9 / peaks["hbm"]})
+        phase_list.append(rec)
     dom = max((k for k in roof_kernels if "bound" in k), key=lambda k: k["ms"], default=None)
     # DRAM traffic per launch comes from an ncu capture (profiles/), never from this run; it is only
     # quoted when that capture was taken from the same library version and workload
@@ -804,6 +829,10 @@ def build_line(args, cfg, world, mode, peaks, kavg, value, ms_step, value_path, 
         "step_tensor_frac": step_flops / (ms_step * 1e-3) / 1e12 / peaks["tf_burst"],
         "step_algorithmic_tflops": step_flops / (ms_step * 1e-3) / 1e12,
         "kernels": roof_kernels,
+        "kernels_note": "per-kernel CUDA-event times with every kernel on ONE stream, one after the other "
+                        "(no programmatic launch overlap, dW and dX each on the whole chip)",
+        "phases": phase_list,
+        "phases_note": "events only between phases: the real schedule, dW next to the dX branch on disjoint CTA pairs",
         "library": version, "env": knobs, "bringup_build": bringup,
     }
 

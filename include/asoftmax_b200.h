@@ -232,8 +232,11 @@ int asm_set_embedding_dtype(asm_head* h, int32_t bytes_per_element);
  * allocation) as long as asm_check_labels / profiling are not used inside the capture. */
 int asm_set_lambda_device(asm_head* h, const float* lambda_dev);
 
-/* Per-kernel device timing for bench.py's roofline: when enabled every kernel of a step is
- * bracketed by CUDA events on the step's stream.  asm_get_profile synchronises on the last
+/* Per-kernel device timing for bench.py's roofline: when enabled (1) every kernel of a step is
+ * bracketed by CUDA events on the step's stream, which also puts them all on that one stream,
+ * one after the other.  enable == 2 records events only between PHASES -- norm kernel, forward
+ * kernel, combine, recompute kernel, then the dW kernel next to the dX branch as one phase -- and
+ * leaves the real schedule (side stream, dW and dX on disjoint CTA pairs) in place.  asm_get_profile synchronises on the last
  * event and writes up to max_n durations (ms) and 32-byte NUL-terminated kernel names;
  * returns the number written (>= 0) or a negative asm_status. */
 int asm_set_profiling(asm_head* h, int enable);

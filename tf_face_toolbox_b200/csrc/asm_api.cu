@@ -50,6 +50,8 @@ struct asm_head {
   int launches = 0;
   // optional per-kernel timing (asm_set_profiling): event i is recorded before kernel i
   bool profiling = false;
+  bool phase_profiling = false;  // asm_set_profiling(h, 2): events only where the main stream serialises anyway, so the
+                                 // real schedule (side stream, dW next to dX) is what gets timed
   static constexpr int kMaxMarks = 16;
   cudaEvent_t ev[kMaxMarks + 1] = {};
   const char* mark_name[kMaxMarks] = {};
@@ -156,8 +158,9 @@ int fail(asm_head* h, int code, const char* fmt, const char* detail) {
   } while (0)
 
 // Counts a kernel launch and, when profiling, records the event that precedes it.
-void mark(asm_head* h, const char* name, cudaStream_t stream) {
+void mark(asm_head* h, const char* name, cudaStream_t stream, bool phase_start = true) {
   h->launches += 1;
+  if (h->phase_profiling && !phase_start) return;      // inside a phase: no event
   if (h->profiling && h->n_marks < asm_head::kMaxMarks) {
     cudaEventRecord(h->ev[h->n_marks], stream);
     h->mark_name[h->n_marks] = name;
@@ -180,7 +183,7 @@ int check_launch(asm_head* h, const char* what) {
 // SMs given to the dW and to the dX kernel (all of them to each unless the two are meant to run
 // side by side: dX forked to the side stream AND a pair split configured)
 bool split_active(const asm_head* h) {
-  return h->dw_pairs > 0 && h->overlap && !h->profiling && h->side != nullptr && h->tc &&
+  return h->dw_pairs > 0 && h->overlap && (!h->profiling || h->phase_profiling) && h->side != nullptr && h->tc &&
          (h->tune.cg_mask & 12) == 12;
 }
 int dw_sms(const asm_head* h) { return split_active(h) ? 2 * h->dw_pairs : h->num_sms; }
@@ -307,7 +310,7 @@ int run_backward(asm_head* h, const float* stats_all, int n_shards, float* loss_
     // read the bf16 copy, which the update never touches, so they may overlap).
     const bool dx_first = !tc && s.opt.kind != 0;
     // the per-kernel profile needs one stream; otherwise fork the dX branch
-    const bool fork = h->overlap && !h->profiling && h->side != nullptr && !dx_first;
+    const bool fork = h->overlap && (!h->profiling || h->phase_profiling) && h->side != nullptr && !dx_first;
     cudaStream_t sx = stream;
     if (fork) {
       cudaEventRecord(h->ev_fork, stream);
@@ -315,15 +318,15 @@ int run_backward(asm_head* h, const float* stats_all, int n_shards, float* loss_
       sx = h->side;
     }
     auto run_dx = [&]() {
-      mark(h, "dx_gemm", sx);
+      mark(h, "dx_gemm", sx, !h->phase_profiling);
       if (tc) launch_umma_dx(s, h->maps, h->tune, dx_sms(h), sx);
       else launch_simt_dx(s, sx);
-      mark(h, tp ? "dx_finish_exchange" : "dx_finish", sx);
+      mark(h, tp ? "dx_finish_exchange" : "dx_finish", sx, !h->phase_profiling);
       if (tp) launch_dx_finish_p2p(s, *tp, sx);
       else launch_dx_finish(s, sx);
     };
     if (dx_first) run_dx();
-    mark(h, "dw_gemm", stream);
+    mark(h, h->phase_profiling ? "dw+dx+dx_finish (side by side)" : "dw_gemm", stream);
     if (tc && s.opt.kind != 0 && h->opt_stream) {
       // opt-in alternative to the fused epilogue: plain dW into a scratch buffer, then one
       // streaming pass over (dW, W, state)
@@ -721,6 +724,7 @@ int asm_set_profiling(asm_head* h, int enable) {
     for (int i = 0; i <= asm_head::kMaxMarks; ++i) CU_TRY(h, cudaEventCreate(&h->ev[i]));
   }
   h->profiling = enable != 0;
+  h->phase_profiling = enable == 2;
   h->n_marks = 0;
   return ASM_OK;
 }
