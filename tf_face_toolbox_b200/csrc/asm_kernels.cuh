@@ -148,7 +148,7 @@ struct Step {
   float* dx_part;            // [KS, B, D] split-K partials of dX
   int KS;
   __nv_bfloat16* Xb;         // [B, D]    bf16 mode;  [B, 3D]  (three planes side by side) when x3
-  __nv_bfloat16* Wb;         // [D, Cp]   bf16 mode;  [D, 3Cp] when x3
+  __nv_bfloat16* Wb;         // bf16 mode: column-blocked [planes][Cp/64][D][64], planes = 3 when x3
   // x3 = 1: fp32 mode on the tensor cores.  Every fp32 operand is split exactly into bf16
   // planes (v = p0 + p1 + p2, p0 = bf16(v), p1 = bf16(v - p0), ...) stored side by side along
   // the inner dimension; a contraction runs as a chain of plane-pair segments accumulated in

@@ -25,28 +25,28 @@ namespace asmh {
 // the W role, which depends on nobody, runs meanwhile.  Publish blocks come first in the grid
 // so that they are dispatched before any block that waits for a peer.
 // ---------------------------------------------------------------------------------------
+// vblock: the block index this call plays (blockIdx.x)
 template <bool VEC2, int PL, int TX, int TY, int U>
-__global__ void __launch_bounds__(256) prep_kernel(Step s, const void* labels, int label_bytes,
-                                                   int nwb, int npub, P2P p) {
+__device__ __forceinline__ void prep_block(const Step& s, const void* labels, int label_bytes,
+                                           int nwb, int npub, const P2P& p, const int vblock,
+                                           float (*red)[2 * TX]) {
   static_assert(TX * TY == 256, "256 threads");
-  pdl_trigger();            // first kernel of the step: nothing to wait for
-  __shared__ float red[TY][2 * TX];
   const int tid = threadIdx.x;
-  if ((int)blockIdx.x < npub) {
+  if (vblock < npub) {
     const unsigned cur = p2p_current_step(p);
     float4* xs = reinterpret_cast<float4*>(p.x(p.rank, cur & 1));
     int* ys = p.y(p.rank, cur & 1);
     const size_t n4 = (size_t)p.b_local * p.D * (s.x_bf16 ? 2 : 4) / 16;     // 16-byte pieces of my rows
-    for (size_t i = blockIdx.x * (size_t)256 + tid; i < n4; i += (size_t)npub * 256)
+    for (size_t i = vblock * (size_t)256 + tid; i < n4; i += (size_t)npub * 256)
       xs[i] = __ldg(reinterpret_cast<const float4*>(p.x_local) + i);
-    for (int i = blockIdx.x * 256 + tid; i < p.b_local; i += npub * 256)
+    for (int i = vblock * 256 + tid; i < p.b_local; i += npub * 256)
       ys[i] = p.y_bytes == 8 ? (int)reinterpret_cast<const long long*>(p.y_local)[i]
                              : reinterpret_cast<const int*>(p.y_local)[i];
     if (block_ticket(p.tickets + 0, (unsigned)npub) == (unsigned)npub - 1 && tid == 0)
       p2p_publish(p, 0, cur);
     return;
   }
-  const int bid = (int)blockIdx.x - npub;
+  const int bid = vblock - npub;
   if (bid < nwb) {
     const int tx = tid % TX, ty = tid / TX;
     const int j0 = (bid * TX + tx) * 2;
@@ -55,8 +55,10 @@ __global__ void __launch_bounds__(256) prep_kernel(Step s, const void* labels, i
       const bool v0 = j0 < s.C, v1 = j0 + 1 < s.C;
       const float* w = s.W + j0;
       constexpr bool BF16 = PL > 0;                 // PL: bf16 planes written (0, 1 or 3)
-      __nv_bfloat16* wb = BF16 ? s.Wb + j0 : nullptr;
-      const size_t wpitch = (size_t)PL * s.Cp;
+      // bf16 copy, COLUMN-BLOCKED [plane][Cp/64][D][64]: the GEMM kernels' 64-class TMA boxes are
+      // contiguous in memory (asm_umma_gemm.cu, wb_row)
+      __nv_bfloat16* wb = BF16 ? s.Wb + (size_t)(j0 >> 6) * s.D * 64 + (j0 & 63) : nullptr;
+      const size_t plane = (size_t)s.D * s.Cp;
       // U rows per trip: all loads are issued before the first use so that U x 8 B per
       // thread are in flight (the bf16 stores would otherwise serialise the loads).
       for (int d0 = ty; d0 < s.D; d0 += TY * U) {
@@ -88,12 +90,12 @@ __global__ void __launch_bounds__(256) prep_kernel(Step s, const void* labels, i
           a0 = fmaf(x0[u], x0[u], a0);
           a1 = fmaf(x1[u], x1[u], a1);
           if (BF16 && d < s.D) {
-            __nv_bfloat162* dst = reinterpret_cast<__nv_bfloat162*>(wb + (size_t)d * wpitch);
+            __nv_bfloat162* dst = reinterpret_cast<__nv_bfloat162*>(wb + (size_t)d * 64);
             float r0 = x0[u], r1 = x1[u];
 #pragma unroll
             for (int p = 0; p < PL; ++p) {             // exact split: residual after each plane
               const __nv_bfloat162 hv = __floats2bfloat162_rn(r0, r1);
-              dst[(size_t)p * (s.Cp / 2)] = hv;
+              dst[(size_t)p * (plane / 2)] = hv;
               r0 -= __low2float(hv);
               r1 -= __high2float(hv);
             }
@@ -219,6 +221,14 @@ __global__ void __launch_bounds__(256) prep_kernel(Step s, const void* labels, i
       s.tgt_f[row] = 0.f;
     }
   }
+}
+
+template <bool VEC2, int PL, int TX, int TY, int U>
+__global__ void __launch_bounds__(256) prep_kernel(Step s, const void* labels, int label_bytes,
+                                                   int nwb, int npub, P2P p) {
+  pdl_trigger();            // first kernel of the step: nothing to wait for
+  __shared__ float red[TY][2 * TX];
+  prep_block<VEC2, PL, TX, TY, U>(s, labels, label_bytes, nwb, npub, p, (int)blockIdx.x, red);
 }
 
 template <int TX, int TY, int U>

@@ -90,7 +90,7 @@ template <int KIND, int CG = 1, int BNT = BN_FULL> struct Geo {
   static constexpr int RES_B = RES ? 8 * A_BYTES : 0;      // resident A block (K <= 512)
   static constexpr int CH_B = 64 * KB * 2;                 // one 64-wide MN-major chunk
   static constexpr int PIPE_B = RES_B + NST * ST_B;
-  static constexpr int AUX_R = RES ? AUX_VEC
+  static constexpr int AUX_R = (RES || KIND == U_FWD) ? AUX_VEC       // forward: the per-tile vectors only
                                : (KIND == U_DW ? 2 * NWB * WB_BUF + (DW_TMA ? 4 * DSTG : 0)
                                                : (NSB == 2 ? AUX_VEC + 2 * AUX_STG : AUX_REGION));
   static constexpr int SMEM = PIPE_B + AUX_BARS + AUX_R + 1024;
@@ -276,6 +276,11 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
           }
           const int kA = A_MN ? k0 : k0 + oa, mA = A_MN ? m0 + oa : m0;
           const int kB = B_MN ? k0 : k0 + ob, nB = B_MN ? n0 + ob : n0;
+          // The bf16 weights are stored COLUMN-BLOCKED, [plane][Cp/64][D][64]: the 64 classes x rows
+          // box of any weight operand is one contiguous piece of memory (8 KB for 64 rows), not 64
+          // rows a whole weight-matrix pitch apart.  Box coordinate: (0, row of the 2-D view
+          // [planes * Cp/64 * D, 64]); for weight operands oa / ob hold the PLANE, not an offset.
+          auto wb_row = [&](int cls0, int d0, int plane) { return (plane * (s.Cp >> 6) + (cls0 >> 6)) * s.D + d0; };
           if (CG == 2) {
             // both CTAs load their A rows and their half of B; all bytes are counted on the
             // leader's full barrier, which only the leader arms
@@ -284,15 +289,22 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
               // A is resident
             } else if (A_MN) {
 #pragma unroll
-              for (int c = 0; c < BM / 64; ++c)
-                ptx::tma_load_2d_cg2(sA + c * CH_B, &mapA, &full[st], mA + c * 64, kA);
+              for (int c = 0; c < BM / 64; ++c) {
+                if (IS_BWDG) ptx::tma_load_2d_cg2(sA + c * CH_B, &mapA, &full[st], 0, wb_row(m0 + c * 64, k0, oa));
+                else ptx::tma_load_2d_cg2(sA + c * CH_B, &mapA, &full[st], mA + c * 64, kA);
+              }
             } else {
               ptx::tma_load_2d_cg2(sA, &mapA, &full[st], kA, mA);
             }
             if (B_MN) {
 #pragma unroll
-              for (int c = 0; c < BN / 128; ++c)
-                ptx::tma_load_2d_cg2(sB + c * CH_B, &mapB, &full[st], nB + (crank * (BN / 128) + c) * 64, kB);
+              for (int c = 0; c < BN / 128; ++c) {
+                if (IS_FWD) ptx::tma_load_2d_cg2(sB + c * CH_B, &mapB, &full[st], 0,
+                                                 wb_row(n0 + (crank * (BN / 128) + c) * 64, k0, ob));
+                else ptx::tma_load_2d_cg2(sB + c * CH_B, &mapB, &full[st], nB + (crank * (BN / 128) + c) * 64, kB);
+              }
+            } else if (KIND == U_DX) {
+              ptx::tma_load_2d_cg2(sB, &mapB, &full[st], 0, wb_row(k0, n0 + crank * (BN / 2), ob));
             } else {
               ptx::tma_load_2d_cg2(sB, &mapB, &full[st], kB, nB + crank * (BN / 2));
             }
@@ -303,15 +315,21 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
             // A is resident
           } else if (A_MN) {
 #pragma unroll
-            for (int c = 0; c < BM / 64; ++c)
-              ptx::tma_load_2d(sA + c * CH_B, &mapA, &full[st], mA + c * 64, kA);
+            for (int c = 0; c < BM / 64; ++c) {
+              if (IS_BWDG) ptx::tma_load_2d(sA + c * CH_B, &mapA, &full[st], 0, wb_row(m0 + c * 64, k0, oa));
+              else ptx::tma_load_2d(sA + c * CH_B, &mapA, &full[st], mA + c * 64, kA);
+            }
           } else {
             ptx::tma_load_2d(sA, &mapA, &full[st], kA, mA);
           }
           if (B_MN) {
 #pragma unroll
-            for (int c = 0; c < BN / 64; ++c)
-              ptx::tma_load_2d(sB + c * CH_B, &mapB, &full[st], nB + c * 64, kB);
+            for (int c = 0; c < BN / 64; ++c) {
+              if (IS_FWD) ptx::tma_load_2d(sB + c * CH_B, &mapB, &full[st], 0, wb_row(n0 + c * 64, k0, ob));
+              else ptx::tma_load_2d(sB + c * CH_B, &mapB, &full[st], nB + c * 64, kB);
+            }
+          } else if (KIND == U_DX) {
+            ptx::tma_load_2d(sB, &mapB, &full[st], 0, wb_row(k0, n0, ob));
           } else {
             ptx::tma_load_2d(sB, &mapB, &full[st], kB, nB);
           }
@@ -380,8 +398,11 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
           for (int h = 0; h < 2; ++h) {
             ptx::mbar_wait(&wempty[h * NWB + buf], ph ^ 1);
             ptx::mbar_expect_tx(&wfull[h * NWB + buf], WB_BUF);
-            ptx::tma_load_2d(wbuf + (h * NWB + buf) * WB_BUF, &mapC, &wfull[h * NWB + buf],
-                             m_idx * BM, n_idx * BN + h * HC + c * 32);
+            const int d0 = n_idx * BN + h * HC + c * 32;
+#pragma unroll
+            for (int qb = 0; qb < 2; ++qb)          // column-blocked weights: [2 blocks][32 d][64 classes]
+              ptx::tma_load_2d(wbuf + (h * NWB + buf) * WB_BUF + qb * (WB_BUF / 2), &mapC, &wfull[h * NWB + buf], 0,
+                               ((m_idx * BM + qb * 64) >> 6) * s.D + d0);
           }
         }
       }
@@ -728,12 +749,13 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
           const uint32_t cc = lt * (BN / 64) + c;             // chunk counter of this half
           const uint32_t buf = cc % NWB, ph = (cc / NWB) & 1;
           const unsigned short* wsm =
-              reinterpret_cast<const unsigned short*>(wbuf + (half * NWB + buf) * WB_BUF) + lane_row;
+              reinterpret_cast<const unsigned short*>(wbuf + (half * NWB + buf) * WB_BUF) +
+              (lane_row >> 6) * (32 * 64) + (lane_row & 63);       // [2 blocks of 64 classes][32 d][64]
           ptx::mbar_wait(&wfull[half * NWB + buf], ph);
           float o[32];
 #pragma unroll
           for (int b = 0; b < 32; ++b)
-            o[b] = fmaf(__uint_as_float(static_cast<uint32_t>(wsm[b * 128]) << 16), coef,
+            o[b] = fmaf(__uint_as_float(static_cast<uint32_t>(wsm[b * 64]) << 16), coef,
                         __uint_as_float(r[b]));
           ptx::mbar_arrive(&wempty[half * NWB + buf]);       // chunk consumed (values in o[])
           const int db = d_first + c * 32;                    // first d of the chunk
@@ -755,6 +777,18 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
               float* dst = s.dW + (size_t)(db + 1) * s.C + j;
 #pragma unroll
               for (int b = 1; b < 32; b += 2) {
+                *dst = o[b];
+                dst += 2 * (size_t)s.C;
+              }
+            }
+            if (dw_sh != 0 && jv && j >= s.C - 2 && db < s.D) {
+              // ... and the even rows END 8 bytes off one: a box clipped there shares its last
+              // 16-byte granule with classes 0 and 1 of the next (odd) row and was seen to
+              // clobber them, so the even-row extent stops two classes early (umma_build_dw_maps)
+              // and the last two classes are written by their owners
+              float* dst = s.dW + (size_t)db * s.C + j;
+#pragma unroll
+              for (int b = 0; b < 32; b += 2) {
                 *dst = o[b];
                 dst += 2 * (size_t)s.C;
               }
@@ -1038,21 +1072,22 @@ bool umma_build_maps(UmmaMaps* m, const Step& s) {
   bool ok = true;
   // x3: the bf16 planes of each operand lie side by side along the inner dimension
   const uint64_t xd = (uint64_t)(s.x3 ? 3 : 1) * s.D;      // Xb [B, D] or [B, 3D]
-  const uint64_t wc = (uint64_t)(s.x3 ? 3 : 1) * s.Cp;     // Wb [D, Cp] or [D, 3Cp]
   const uint64_t gp = (uint64_t)(s.x3 ? 2 : 1) * s.Bp;     // G'' pitch: [Cp, Bp] or [Cp, 2Bp] (two planes)
   const uint64_t gi = s.x3 ? gp : (uint64_t)s.B;           // inner extent (batch): clipped at B, planes at Bp
   ok &= encode_map(&m->xb_k, s.Xb, xd, s.B, xd, 64, 128);     // A of FWD  (K-major, M = batch)
   ok &= encode_map(&m->xb_k256, s.Xb, xd, s.B, xd, 64, 256);  // B of BWDG (K-major, N = batch)
   ok &= encode_map(&m->xb_mn, s.Xb, xd, s.B, xd, 64, 64);     // B of DW   (MN-major, N = d)
-  ok &= encode_map(&m->wb_mn, s.Wb, wc, s.D, wc, 64, 64);     // B of FWD / A of BWDG (MN-major)
-  ok &= encode_map(&m->wb_mn32, s.Wb, wc, s.D, wc, 64, 32);   // B of FWDR (32-deep K stages)
-  ok &= encode_map(&m->wb_k, s.Wb, wc, s.D, wc, 64, 256);     // B of DX   (K-major, N = d)
-  ok &= encode_map(&m->wb_k128, s.Wb, wc, s.D, wc, 64, 128);  // B half of DX in a CTA pair
+  // the bf16 weights, column-blocked [planes * Cp/64 * D rows][64 classes]: every box is contiguous
+  const uint64_t wrows = (uint64_t)(s.x3 ? 3 : 1) * (s.Cp / 64) * s.D;
+  ok &= encode_map(&m->wb_mn, s.Wb, 64, wrows, 64, 64, 64);     // B of FWD / A of BWDG (MN-major)
+  ok &= encode_map(&m->wb_mn32, s.Wb, 64, wrows, 64, 64, 32);   // B of FWDR (32-deep K stages)
+  ok &= encode_map(&m->wb_k, s.Wb, 64, wrows, 64, 64, 256);     // B of DX   (K-major, N = d)
+  ok &= encode_map(&m->wb_k128, s.Wb, 64, wrows, 64, 64, 128);  // B half of DX in a CTA pair
   ok &= encode_map(&m->g_k, s.G, gi, s.Cp, gp, 64, 128);      // A of DW   (K-major: K = batch, M = class)
   ok &= encode_map(&m->g_mn, s.G, gi, s.Cp, gp, 64, 64);      // A of DX   (MN-major: M = batch, K = class)
   ok &= encode_map(&m->g_st, s.G, gi, s.Cp, gp, 32, 128, false, false, true);   // BWDG store (64B swizzle)
   ok &= encode_map(&m->g_st32, s.G, gi, s.Cp, gp, 32, 32, false, false, true);  // ... one warp's 32 classes
-  ok &= encode_map(&m->wb_box, s.Wb, wc, s.D, wc, 128, 32, false); // DW weight chunks
+  ok &= encode_map(&m->wb_box, s.Wb, 64, wrows, 64, 64, 32, false); // DW weight chunks (two per 128 classes)
   // dX partials [KS][B][D] fp32 (D % 4 == 0, so every stride is a multiple of 16 bytes)
   m->dx_ok = encode_map3_f32(&m->dx_st, s.dx_part, (uint64_t)s.D, (uint64_t)s.B, (uint64_t)(s.KS > 0 ? s.KS : 1)) ? 1 : 0;
   return ok;
@@ -1068,7 +1103,8 @@ void umma_build_dw_maps(UmmaMaps* m, const Step& s) {
   // a TMA store must start on a 16-byte boundary: odd rows begin 4C bytes into a view row, so
   // for C % 4 == 2 their box starts two classes later and is four classes narrower
   const uint32_t odd_box = (s.C & 3) ? 124 : 128;
-  bool ok = encode_map(&m->dw_even, s.dW, C, rows, 2 * C, 128, 16, false, true);
+  // ... and must not be CLIPPED off one either (see the dW epilogue): even rows stop at C - 2
+  bool ok = encode_map(&m->dw_even, s.dW, (s.C & 3) ? C - 2 : C, rows, 2 * C, 128, 16, false, true);
   ok &= encode_map(&m->dw_odd, s.dW, 2 * C, rows, 2 * C, odd_box, 16, false, true);
   m->dw_ok = ok ? 1 : 0;
 }
@@ -1174,7 +1210,7 @@ void launch_umma_forward(const Step& s, const UmmaMaps& m, const UmmaTuning& tu,
   g.nt = s.Cp / bn;
   const int units = umma_forward_grid(s.B, s.Cp, num_sms, cg, bn) / cg;
   if (bn == 128) {              // narrow tiles: more units for shards that do not fill the pairs
-    set_segments(g, s.x3 != 0, (s.D + BK - 1) / BK, kSegHi, kSegLo, x3_segments(), s.D, s.Cp);
+    set_segments(g, s.x3 != 0, (s.D + BK - 1) / BK, kSegHi, kSegLo, x3_segments(), s.D, 1);
     launch_k<U_FWD, 2, 128>(units, m.xb_k, m.wb_mn, m.wb_mn, s, g, st);
     return;
   }
@@ -1195,7 +1231,7 @@ void launch_umma_forward(const Step& s, const UmmaMaps& m, const UmmaTuning& tu,
     return;
   }
 #endif
-  set_segments(g, s.x3 != 0, (s.D + BK - 1) / BK, kSegHi, kSegLo, x3_segments(), s.D, s.Cp);
+  set_segments(g, s.x3 != 0, (s.D + BK - 1) / BK, kSegHi, kSegLo, x3_segments(), s.D, 1);
   if (cg == 2) launch_k<U_FWD, 2>(units, m.xb_k, m.wb_mn, m.wb_mn, s, g, st);
   else launch_k<U_FWD, 1>(units, m.xb_k, m.wb_mn, m.wb_mn, s, g, st);
 }
@@ -1208,7 +1244,7 @@ void launch_umma_bwdg(const Step& s, const UmmaMaps& m, const UmmaTuning& tu, in
   const int bn = umma_tile_width(tu, cg, (long long)g.mt * ((s.B + BN_FULL - 1) / BN_FULL), num_sms);
   g.nt = (s.B + bn - 1) / bn;
   // A = weights, B = embeddings: the same plane pairs with the roles swapped
-  set_segments(g, s.x3 != 0, (s.D + BK - 1) / BK, kSegLo, kSegHi, x3_segments(), s.Cp, s.D);
+  set_segments(g, s.x3 != 0, (s.D + BK - 1) / BK, kSegLo, kSegHi, x3_segments(), 1, s.D);
   g.rev = tu.l2_order ? 1 : 0;  // the forward kernel swept the classes upwards: start where it stopped
   const int units = min(g.mt * g.nt, num_sms / cg);
   if (bn == 128) launch_k<U_BWDG, 2, 128>(units, m.wb_mn, m.xb_mn, m.g_st, s, g, st, &m.g_st32);   // X box: 64 rows per CTA
@@ -1260,7 +1296,7 @@ void launch_umma_dx(const Step& s, const UmmaMaps& m, const UmmaTuning& tu, int 
   g.mt = ((s.B + BM - 1) / BM + cg - 1) / cg;
   g.nt = (s.D + BN - 1) / BN;
   set_segments(g, s.x3 != 0, (s.Cp + BK - 1) / BK, kSegG, kSegO, x3_segments() < 5 ? x3_segments() : 5,
-               s.Bp, s.Cp);
+               s.Bp, 1);
   g.ks = s.KS;
   g.kb_per = (g.kb_total + g.ks - 1) / g.ks;
   if (tu.l2_order && !s.x3) {   // all splits sweep the classes together, downwards (DW went up) --
