@@ -48,6 +48,11 @@ def check_against_oracle(inp, m, lam, mode, logits=False, cos_min=0.9999, loss_f
         # element errors stay below a few 1e-6 of the matrix scale
         np.testing.assert_allclose(dX, r.dX, rtol=2e-3, atol=4e-6 * np.abs(r.dX).max() + 1e-12)
         np.testing.assert_allclose(dW, r.dW, rtol=2e-3, atol=1e-5 * np.abs(r.dW).max() + 1e-12)
+    else:
+        # bf16 mode: every element within 3 % of the matrix scale (a cosine over the whole matrix
+        # does not notice one wrong column)
+        ex, ew = np.abs(dX - r.dX).max() / np.abs(r.dX).max(), np.abs(dW - r.dW).max() / np.abs(r.dW).max()
+        assert ex <= 3e-2 and ew <= 3e-2, (ex, ew, int(np.abs(dW - r.dW).max(axis=0).argmax()))
     if logits:
         tol = 1e-4 if mode == "fp32" else 0.35
         np.testing.assert_allclose(f, r.logits, atol=tol, rtol=1e-4 if mode == "fp32" else 2e-2)
@@ -537,7 +542,9 @@ def test_bf16_cfg5_full_size_vs_streamed_oracle():
     assert abs(float(loss) - r.loss) <= 2e-3 * r.loss
     assert cosine(dX.cpu().numpy(), r.dX) >= 0.9999
     for (lo, hi), want in r.dW.items():
-        assert cosine(dW[:, lo:hi].cpu().numpy(), want) >= 0.9999, (lo, hi)
+        got = dW[:, lo:hi].cpu().numpy()
+        assert cosine(got, want) >= 0.9999, (lo, hi)
+        assert np.abs(got - want).max() <= 2e-2 * np.abs(want).max(), (lo, hi)
 
 
 def test_bf16_cfg4_shard_geometry_vs_streamed_oracle():
@@ -569,7 +576,9 @@ def test_bf16_cfg4_shard_geometry_vs_streamed_oracle():
     assert cosine(dX.cpu().numpy(), r.dX) >= 0.9999
     for (lo, hi), want in r.dW.items():
         base = 0 if lo < 125000 else 125000
-        assert cosine(dWs[base][:, lo - base:hi - base].cpu().numpy(), want) >= 0.9999, (lo, hi)
+        got = dWs[base][:, lo - base:hi - base].cpu().numpy()
+        assert cosine(got, want) >= 0.9999, (lo, hi)
+        assert np.abs(got - want).max() <= 2e-2 * np.abs(want).max(), (lo, hi)
 
 
 def test_dw_rows_that_end_off_a_16_byte_boundary():
