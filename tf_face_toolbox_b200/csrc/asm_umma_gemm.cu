@@ -77,7 +77,9 @@ enum { U_FWD = 0, U_BWDG = 1, U_DW = 2, U_DX = 3, U_FWDR = 4, U_DWOPT = 5, U_DWF
 template <int KIND, int CG = 1, int BNT = BN_FULL> struct Geo {
   static constexpr bool RES = (KIND == U_FWDR);
   static constexpr int KB = (RES && CG == 1) ? 32 : BK;    // K elements per pipeline stage
-  static constexpr int NWB = 2;                            // weight-chunk buffers per column half
+  // weight-chunk buffers per column half (4 buffers paid for with one of the dW kernel's four
+  // operand stages measured SLOWER: 83 vs 78 us at config 3)
+  static constexpr int NWB = 2;
   // the dW kernel of a CTA pair stages its output in shared memory and leaves through TMA
   // stores (two [32 d x 128 classes] fp32 buffers per column half), paid for with two operand stages
   static constexpr bool DW_TMA = (KIND == U_DW && CG == 2);
@@ -162,7 +164,9 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
   uint64_t* tempty = tfull + 2;                                       // [2]
   uint64_t* wfull = tempty + 2;                                       // DW: [half][buf]; FWDR: [0] = X resident
   uint64_t* wempty = wfull + 8;                                       // DW: [half][buf]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(wempty + 8);
+  uint64_t* sfull = wempty + 8;                                       // DW (pairs): [half][2] staging buffer filled
+  uint64_t* sempty = sfull + 4;                                       // DW (pairs): [half][2] ... drained by its TMA store
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(sempty + 4);
   constexpr int NWB = G_::NWB;
   float* vec0 = reinterpret_cast<float*>(smem + PIPE_B + AUX_BARS);   // [2][BN_FULL]
   float* vec1 = vec0 + 2 * BN_FULL;
@@ -193,6 +197,10 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
     for (int i = 0; i < 8; ++i) {
       ptx::mbar_init(&wfull[i], 1);
       ptx::mbar_init(&wempty[i], 128);
+    }
+    for (int i = 0; i < 4; ++i) {
+      ptx::mbar_init(&sfull[i], 4);                          // one arrival per epilogue warp of the half
+      ptx::mbar_init(&sempty[i], 1);
     }
     ptx::fence_barrier_init();
   }
@@ -380,6 +388,45 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
         // accumulator ready for the epilogue (of both CTAs of a pair)
         if (CG == 2) ptx::umma_commit_cg2(&tfull[a]); else ptx::umma_commit(&tfull[a]);
       }
+    }
+  } else if (warp == 2) {
+    // ------------------------------------------------------------ DW (pairs): dW store issuer
+    // One thread per column half takes the staged [32 d x 128 classes] chunks off the epilogue
+    // warps' hands: it waits for a staging buffer to be full, issues its two TMA stores (even /
+    // odd d rows), waits until they have READ the buffer and hands it back.  The epilogue
+    // warps never wait for a store, only -- two chunks later -- for the buffer.
+    if (G_::DW_TMA && g.dw_tma && lane < 2 && !ASM_DBG(g.debug_flags, 1)) {
+      const int half = lane;
+      const int dw_sh = g.dw_shift;
+      // nothing reads dW inside the step: mark its lines evict-first so that they do not push
+      // the operands the next kernels read (G'', the bf16 weights) out of L2
+      uint64_t store_policy = 0;
+      if (g.store_evict_first) store_policy = ptx::policy_evict_first();
+      uint32_t cc = 0;
+      for (int u = pair_id; u < total; u += npairs) {
+        int z, m_idx, n_idx;
+        decode(u, z, m_idx, n_idx);
+        const int m0 = (m_idx * CG + crank) * BM, n0 = n_idx * BN;
+        for (int c = 0; c < BN / 64; ++c, ++cc) {
+          const uint32_t sb = cc & 1, sph = (cc >> 1) & 1;
+          ptx::mbar_wait(&sfull[half * 2 + sb], sph);
+          const int db = n0 + half * HC + c * 32;             // first d of the chunk
+          if (db < s.D) {                                     // D % 32 == 0 in bf16 mode
+            const uint8_t* src = dstg + half * 2 * DSTG + sb * DSTG;
+            if (g.store_evict_first) {
+              ptx::tma_store_2d_hint(&mapD, src, m0, db >> 1, store_policy);                            // even d
+              ptx::tma_store_2d_hint(&mapE, src + DSTG / 2, s.C + m0 + dw_sh, db >> 1, store_policy);   // odd d
+            } else {
+              ptx::tma_store_2d(&mapD, src, m0, db >> 1);
+              ptx::tma_store_2d(&mapE, src + DSTG / 2, s.C + m0 + dw_sh, db >> 1);
+            }
+            ptx::bulk_commit();
+            ptx::bulk_wait_read0();
+          }
+          ptx::mbar_arrive(&sempty[half * 2 + sb]);
+        }
+      }
+      ptx::bulk_wait0();
     }
   } else if (warp == 3) {
     // ------------------------------------------------------------ DW: weight-chunk producer
@@ -738,11 +785,6 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
         const int dw_op = 128 - 2 * dw_sh;                    // classes per odd-row box
         const bool dw_edge = dw_sh != 0 && (lane_row < dw_sh || lane_row >= 128 - dw_sh);
         uint8_t* dstg_half = dstg + half * 2 * DSTG;
-        const bool leader = (threadIdx.x == 128 + half * 128);
-        // nothing reads dW inside the step: mark its lines evict-first so that they do not push
-        // the operands the next kernels read (G'', the bf16 weights) out of L2
-        uint64_t store_policy = 0;
-        if (dw_tma && leader && g.store_evict_first) store_policy = ptx::policy_evict_first();
         ptx::mbar_wait(&tfull[a], aph);
         ptx::tc_fence_after();
         auto process = [&](const uint32_t (&r)[32], int c) {
@@ -760,9 +802,9 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
           ptx::mbar_arrive(&wempty[half * NWB + buf]);       // chunk consumed (values in o[])
           const int db = d_first + c * 32;                    // first d of the chunk
           if (dw_tma) {
-            // before the barrier of chunk c the leader confirms that the stores of chunk c-1
-            // have drained their buffer -- the buffer chunk c+1 writes after that barrier
-            if (leader) ptx::bulk_wait_read0();
+            // the staging buffer is free again once the stores of chunk c-2 have read it
+            // (warp 2 hands it back)
+            ptx::mbar_wait(&sempty[half * 2 + (cc & 1)], ((cc >> 1) & 1) ^ 1);
             float* sbe = reinterpret_cast<float*>(dstg_half + (c & 1) * DSTG) + lane_row;
             float* sbo = reinterpret_cast<float*>(dstg_half + (c & 1) * DSTG + DSTG / 2) + (lane_row - dw_sh);
 #pragma unroll
@@ -794,18 +836,8 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
               }
             }
             ptx::fence_proxy_async();                         // generic writes -> async proxy
-            named_bar_sync(2 + half, 128);
-            if (leader && db < s.D) {                         // D % 32 == 0 in bf16 mode
-              const uint8_t* src = dstg_half + (c & 1) * DSTG;
-              if (g.store_evict_first) {
-                ptx::tma_store_2d_hint(&mapD, src, m0, db >> 1, store_policy);                            // even d
-                ptx::tma_store_2d_hint(&mapE, src + DSTG / 2, s.C + m0 + dw_sh, db >> 1, store_policy);   // odd d
-              } else {
-                ptx::tma_store_2d(&mapD, src, m0, db >> 1);
-                ptx::tma_store_2d(&mapE, src + DSTG / 2, s.C + m0 + dw_sh, db >> 1);
-              }
-              ptx::bulk_commit();
-            }
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&sfull[half * 2 + (cc & 1)]);    // warp 2 issues the stores
           } else if (jv && db < s.D) {
             float* dst = s.dW + (size_t)db * s.C + j;
 #pragma unroll
@@ -956,7 +988,7 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
       s.part[(size_t)fwd_row * s.NT + (pair_id / g.mt) * 2 + half] = make_float2(run_m, run_z);
   }
 
-  if ((IS_BWDG || G_::DW_TMA || KIND == U_DX) && warp >= 4 && lane == 0) ptx::bulk_wait0();
+  if ((IS_BWDG || KIND == U_DX) && warp >= 4 && lane == 0) ptx::bulk_wait0();
   ptx::tc_fence_before();
   __syncthreads();
   if (CG == 2) ptx::cluster_sync_all();       // the peer may still be read / signalled by the leader
