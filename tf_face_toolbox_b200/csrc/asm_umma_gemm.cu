@@ -47,7 +47,6 @@ constexpr int B_BYTES = BN * BK * 2;           // 32 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES; // 48 KB
 constexpr int CHUNK_BYTES = 64 * BK * 2;       // one 64-wide MN-major chunk: 8 KB
 constexpr int NUM_THREADS = 384;
-constexpr int EPI_THREADS = 256;
 constexpr int AUX_BARS = 512;                  // barriers + tmem ptr
 constexpr int AUX_VEC = 3 * 2 * BN * 4;        // per-tile vectors: 3 arrays x 2 stages x 256
 constexpr int STG_HALF = 32 * 128 * 2;         // G'' staging per column half: 128 classes x 32 batch rows (bf16)
@@ -74,8 +73,20 @@ enum { U_FWD = 0, U_BWDG = 1, U_DW = 2, U_DX = 3, U_FWDR = 4, U_DWOPT = 5, U_DWF
 // CG = 2: a CTA pair (cluster of 2, cta_group::2) computes one 256 x 256 tile; each CTA
 // stages its own 128 A rows and HALF of the B tile, so a stage is 32 KB and the ring is 6 deep.
 // BNT: tile width along N (256, or 128 for shards whose unit count does not fill the pairs)
+#ifndef ASM_FWD_EPI16
+#define ASM_FWD_EPI16 1
+#endif
+constexpr bool FWD_EPI16 = ASM_FWD_EPI16 != 0;
 template <int KIND, int CG = 1, int BNT = BN_FULL> struct Geo {
   static constexpr bool RES = (KIND == U_FWDR);
+  // Epilogue warps.  The epilogues, not the MMAs, bound these kernels (the light dX epilogue
+  // reaches 83 % of the tensor pipe, the forward one 62 %): each scheduler hosts only two
+  // epilogue warps, which spend ~8 cycles per issued instruction on dependency and queue
+  // latencies.  The forward kernel of a CTA pair therefore runs SIXTEEN epilogue warps -- four
+  // per TMEM lane quarter, 64 accumulator columns each -- with single-buffered TMEM loads to
+  // stay inside 96 registers.
+  static constexpr int EPIW = (KIND == U_FWD && CG == 2 && BNT == 256 && FWD_EPI16) ? 16 : 8;
+  static constexpr int NTHREADS = 128 + 32 * EPIW;
   static constexpr int KB = (RES && CG == 1) ? 32 : BK;    // K elements per pipeline stage
   // weight-chunk buffers per column half (4 buffers paid for with one of the dW kernel's four
   // operand stages measured SLOWER: 83 vs 78 us at config 3)
@@ -130,13 +141,16 @@ __device__ __noinline__ float fwd_target(float* tgt_s, float* tgt_f, const float
 }  // namespace
 
 template <int KIND, int CG = 1, int BNT = BN_FULL>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__((Geo<KIND, CG, BNT>::NTHREADS), 1)
 umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
             const __grid_constant__ CUtensorMap mapC, const __grid_constant__ CUtensorMap mapD,
             const __grid_constant__ CUtensorMap mapE, Step s, UmmaArgs g) {
   using G_ = Geo<KIND, CG, BNT>;
   constexpr int BN = BNT;                 // tile width of this instantiation (shadows the default)
-  constexpr int HC = BN / 2;              // accumulator columns per epilogue half
+  constexpr int EPIW = G_::EPIW;          // epilogue warps (8, or 16 in the paired forward kernel)
+  constexpr int NQ = EPIW / 4;            // column groups ("halves" below): 2, or 4
+  constexpr int HC = BN / NQ;             // accumulator columns per column group
+  constexpr int EPI_THREADS = 32 * EPIW;
   static_assert(BNT == 256 || BNT == 128, "tile width");
   static_assert(BNT == 256 || (KIND != U_FWDR && KIND != U_BWDG1), "narrow tiles: main kinds only");
   pdl_trigger();      // the next kernel's CTAs may take over SMs as this grid's tail drains
@@ -192,7 +206,7 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&tfull[a], 1);
-      ptx::mbar_init(&tempty[a], (EPI_THREADS / 32) * CG);   // one arrival per epilogue warp
+      ptx::mbar_init(&tempty[a], EPIW * CG);                 // one arrival per epilogue warp
     }
     for (int i = 0; i < 8; ++i) {
       ptx::mbar_init(&wfull[i], 1);
@@ -354,18 +368,33 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
       const uint32_t stepB = B_MN ? g.kstep_mn : 32u;
       uint32_t it = 0, lt = 0;
       if (RES && pair_id < total) ptx::mbar_wait(&wfull[0], 0);   // resident Xb landed
+#ifdef ASM_TIMING
+      long long t_tempty = 0, t_full = 0, t_all = clock64();
+#endif
       for (int u = pair_id; u < total; u += npairs, ++lt) {
         const int z = u / tiles_mn;
         const int nk = kcount(z);
         const uint32_t a = lt & 1, aph = (lt >> 1) & 1;
+#ifdef ASM_TIMING
+        long long t0 = clock64();
+#endif
         ptx::mbar_wait(&tempty[a], aph ^ 1);
+#ifdef ASM_TIMING
+        t_tempty += clock64() - t0;
+#endif
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + a * BN_FULL;
         for (int ki = 0; ki < nk; ++ki, ++it) {
           const int kb = RES ? kblock(z, ki) : 0;     // only the resident-A variant addresses by kb
           const int st = it % NST;
           const uint32_t ph = (it / NST) & 1;
+#ifdef ASM_TIMING
+          long long t1 = clock64();
+#endif
           ptx::mbar_wait(&full[st], ph);
+#ifdef ASM_TIMING
+          t_full += clock64() - t1;
+#endif
           ptx::tc_fence_after();
           // resident A: 64-wide K blocks of 16 KB; stage kb covers K = [32 kb, 32 kb + 32)
           const uint32_t aA = RES ? ptx::smem_u32(smem + ((kb * KB) >> 6) * A_BYTES) + ((kb * KB) & 63) * 2u
@@ -388,6 +417,11 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
         // accumulator ready for the epilogue (of both CTAs of a pair)
         if (CG == 2) ptx::umma_commit_cg2(&tfull[a]); else ptx::umma_commit(&tfull[a]);
       }
+#ifdef ASM_TIMING
+      if (pair_id == 0 || pair_id == npairs / 2)
+        printf("TIMING kind %d pair %d tiles %u: mma warp total %lld cyc, wait tempty %lld, wait full %lld\n", KIND,
+               pair_id, lt, clock64() - t_all, t_tempty, t_full);
+#endif
     }
   } else if (warp == 2) {
     // ------------------------------------------------------------ DW (pairs): dW store issuer
@@ -494,7 +528,7 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
       int pz, pm, pn;
       decode(pu, pz, pm, pn);
       pm = pm * CG + crank;
-      if (IS_FWD) pre0 = s.inv_c[pn * BN + (BN == BN_FULL ? et : (et & (BN - 1)))];
+      if (IS_FWD) pre0 = s.inv_c[pn * BN + (et & (BN - 1))];
       if (IS_BWDG) {
         const int i = pn * BN + et;
         const bool iv = i < s.B;
@@ -526,12 +560,22 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
         else ptx::mbar_arrive(&tempty[a]);
       }
     };
+#ifdef ASM_TIMING
+    long long e_all = clock64(), e_wait = 0;
+#endif
     for (int u = pair_id; u < total; u += npairs, ++lt) {
       int z, m_idx, n_idx;
       decode(u, z, m_idx, n_idx);
       m_idx = m_idx * CG + crank;
       const int m0 = m_idx * BM, n0 = n_idx * BN;
       const uint32_t a = lt & 1, aph = (lt >> 1) & 1;
+#ifdef ASM_TIMING
+      {   // time this warp would wait for the accumulator (measured before the real waits below)
+        long long t0 = clock64();
+        ptx::mbar_wait(&tfull[a], aph);
+        e_wait += clock64() - t0;
+      }
+#endif
       const uint32_t taddr =
           tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + a * BN_FULL + col0;
       float* v0 = vec0 + a * BN_FULL;
@@ -550,24 +594,35 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
       // to the MMA warp as soon as the last chunk is in registers.  The chunk body is
       // instantiated twice only (r0 / r1) to keep the kernel inside the instruction cache.
 #define ASM_EPILOGUE_CHUNKS(process)                       \
+      if (EPIW == 16) {                                    \
+        /* two chunks per warp, one register buffer */    \
+        ptx::tmem_ld32(taddr, r0);                         \
+        ptx::tmem_ld_wait_dep(r0);                         \
+        process(r0, 0);                                    \
+        ptx::tmem_ld32(taddr + 32, r0);                    \
+        ptx::tmem_ld_wait_dep(r0);                         \
+        release_acc(a);                                    \
+        process(r0, 1);                                    \
+      } else {                                             \
       ptx::tmem_ld32(taddr, r0);                           \
       _Pragma("unroll 1")                                  \
-      for (int cp = 0; cp < BN / 128; ++cp) {              \
+      for (int cp = 0; cp < HC / 64; ++cp) {               \
         ptx::tmem_ld_wait_dep(r0);                         \
         ptx::tmem_ld32(taddr + cp * 64 + 32, r1);          \
         process(r0, cp * 2);                               \
         ptx::tmem_ld_wait_dep(r1);                         \
-        if (cp + 1 < BN / 128) {                           \
+        if (cp + 1 < HC / 64) {                            \
           ptx::tmem_ld32(taddr + 64, r0);                  \
         } else {                                           \
           release_acc(a);                                  \
         }                                                  \
         process(r1, cp * 2 + 1);                           \
+      }                                                    \
       }
 
       if (IS_FWD) {
         // ---- thread = batch row, columns = classes.  Stage 1/c_j for the tile in smem.
-        v0[et] = pre0;
+        if (et < BN) v0[et] = pre0;
         prefetch_tile(u + npairs);
         const int row = m0 + lane_row;
         const bool rv = row < s.B;
@@ -984,8 +1039,13 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
       }
 #undef ASM_EPILOGUE_CHUNKS
     }
+#ifdef ASM_TIMING
+    if ((pair_id == 0 || pair_id == npairs / 2) && crank == 0 && lane == 0 && (warp == 4 || warp == 11))
+      printf("TIMING kind %d pair %d warp %d: epilogue total %lld cyc, wait tfull %lld\n", KIND, pair_id, warp,
+             clock64() - e_all, e_wait);
+#endif
     if (IS_FWD && fwd_row >= 0)
-      s.part[(size_t)fwd_row * s.NT + (pair_id / g.mt) * 2 + half] = make_float2(run_m, run_z);
+      s.part[(size_t)fwd_row * s.NT + (pair_id / g.mt) * NQ + half] = make_float2(run_m, run_z);
   }
 
   if ((IS_BWDG || KIND == U_DX) && warp >= 4 && lane == 0) ptx::bulk_wait0();
@@ -1072,7 +1132,9 @@ int umma_forward_grid(int B, int Cp, int num_sms, int cg, int bn) {
 int umma_forward_tiles(int B, int Cp, int num_sms, int cg, int bn) {
   const int c = fwd_cg(B, cg);
   const int mt = ((B + BM - 1) / BM + c - 1) / c;
-  return 2 * (umma_forward_grid(B, Cp, num_sms, cg, bn) / c / mt);
+  // one (max, sum-exp) partial per column group of a CTA: 2, or 4 with sixteen epilogue warps
+  const int nq = (c == 2 && bn == 256 ? Geo<U_FWD, 2, 256>::EPIW : 8) / 4;
+  return nq * (umma_forward_grid(B, Cp, num_sms, cg, bn) / c / mt);
 }
 int umma_q_parts(int B, int bn) { return 2 * ((B + bn - 1) / bn); }    // one partial per column half of a batch tile
 
@@ -1201,7 +1263,7 @@ void launch_k(int units, const CUtensorMap& a, const CUtensorMap& b, const CUten
   if (units <= 0) return;
   // DW follows an event record (the dX fork), everything else follows a kernel directly
   const bool pdl = s.pdl != 0 && KIND != U_DW && KIND != U_DWOPT && KIND != U_DWF;
-  launch_pdl(umma_kernel<KIND, CG, BNT>, dim3(units * CG), dim3(NUM_THREADS), Geo<KIND, CG, BNT>::SMEM, st,
+  launch_pdl(umma_kernel<KIND, CG, BNT>, dim3(units * CG), dim3(Geo<KIND, CG, BNT>::NTHREADS), Geo<KIND, CG, BNT>::SMEM, st,
              pdl, CG, a, b, c, d ? *d : c, e ? *e : c, s, g);
 }
 }  // namespace
