@@ -102,6 +102,7 @@ Layout make_layout(const asm_config& c, int num_sms) {
   L.NT = (L.Cp + 127) / 128;
   if (L.NT < 2 * num_sms) L.NT = 2 * num_sms;   // tcgen05 forward: 2 partials per CTA
   L.MT = 2 * (int)((B + 127) / 128);      // two per batch tile, down to 128-row tiles
+  if (L.MT < 4 * (int)((B + 255) / 256)) L.MT = 4 * (int)((B + 255) / 256);   // four per 256-row tile (sixteen epilogue warps)
   // dX split-K partial capacity: the larger of both paths at B_max, but never less than
   // what a single 128-row tile would use (KS grows when B shrinks).
   const int ks_simt = simt_dx_splits(c.B_max, c.D, L.Cp);
@@ -213,7 +214,7 @@ int run_forward(asm_head* h, const float* X, int B, const void* labels, int labe
     // column half of a batch tile
     const int bcg = (h->tune.cg_mask & 2) ? 2 : 1;
     const long long bunits = (long long)(s.Cp / (128 * bcg)) * ((B + 255) / 256);
-    s.MT = h->tc ? umma_q_parts(B, umma_tile_width(h->tune, bcg, bunits, h->num_sms))
+    s.MT = h->tc ? umma_q_parts(B, umma_tile_width(h->tune, bcg, bunits, h->num_sms), bcg)
                  : (B + kRowTileHost - 1) / kRowTileHost;
   }
   h->launches = 0;

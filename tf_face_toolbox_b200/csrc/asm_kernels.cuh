@@ -240,7 +240,7 @@ void umma_build_dw_maps(UmmaMaps* m, const Step& s);
 int umma_tile_width(const UmmaTuning& tu, int cg, long long units256, int num_sms);
 int umma_forward_tiles(int B, int Cp, int num_sms, int cg, int bn = 256);
 int umma_forward_grid(int B, int Cp, int num_sms, int cg, int bn = 256);
-int umma_q_parts(int B, int bn = 256);
+int umma_q_parts(int B, int bn, int cg);
 int umma_dx_splits(int B, int D, int Cp, int num_sms, int cg);
 void launch_umma_forward(const Step& s, const UmmaMaps& m, const UmmaTuning& tu, int num_sms,
                          cudaStream_t st);

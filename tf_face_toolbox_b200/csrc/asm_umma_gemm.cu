@@ -77,15 +77,20 @@ enum { U_FWD = 0, U_BWDG = 1, U_DW = 2, U_DX = 3, U_FWDR = 4, U_DWOPT = 5, U_DWF
 #define ASM_FWD_EPI16 1
 #endif
 constexpr bool FWD_EPI16 = ASM_FWD_EPI16 != 0;
+#ifndef ASM_BWDG_EPI16
+#define ASM_BWDG_EPI16 1
+#endif
+constexpr bool BWDG_EPI16 = ASM_BWDG_EPI16 != 0;
 template <int KIND, int CG = 1, int BNT = BN_FULL> struct Geo {
   static constexpr bool RES = (KIND == U_FWDR);
   // Epilogue warps.  The epilogues, not the MMAs, bound these kernels (the light dX epilogue
   // reaches 83 % of the tensor pipe, the forward one 62 %): each scheduler hosts only two
   // epilogue warps, which spend ~8 cycles per issued instruction on dependency and queue
-  // latencies.  The forward kernel of a CTA pair therefore runs SIXTEEN epilogue warps -- four
-  // per TMEM lane quarter, 64 accumulator columns each -- with single-buffered TMEM loads to
-  // stay inside 96 registers.
-  static constexpr int EPIW = (KIND == U_FWD && CG == 2 && BNT == 256 && FWD_EPI16) ? 16 : 8;
+  // latencies.  The forward and the recompute kernel of a CTA pair therefore run SIXTEEN
+  // epilogue warps -- four per TMEM lane quarter, 64 accumulator columns each -- with
+  // single-buffered TMEM loads (and, in the recompute kernel, one G'' staging block per warp) to
+  // stay inside 96 registers and the shared memory.
+  static constexpr int EPIW = ((KIND == U_FWD && FWD_EPI16) || (KIND == U_BWDG && BWDG_EPI16)) && CG == 2 && BNT == 256 ? 16 : 8;
   static constexpr int NTHREADS = 128 + 32 * EPIW;
   static constexpr int KB = (RES && CG == 1) ? 32 : BK;    // K elements per pipeline stage
   // weight-chunk buffers per column half (4 buffers paid for with one of the dW kernel's four
@@ -105,7 +110,7 @@ template <int KIND, int CG = 1, int BNT = BN_FULL> struct Geo {
   static constexpr int PIPE_B = RES_B + NST * ST_B;
   static constexpr int AUX_R = (RES || KIND == U_FWD) ? AUX_VEC       // forward: the per-tile vectors only
                                : (KIND == U_DW ? 2 * NWB * WB_BUF + (DW_TMA ? 4 * DSTG : 0)
-                                               : (NSB == 2 ? AUX_VEC + 2 * AUX_STG : AUX_REGION));
+                                               : (NSB == 2 ? AUX_VEC + 2 * AUX_STG + (EPIW == 16 ? 2048 : 0) : AUX_REGION));
   static constexpr int SMEM = PIPE_B + AUX_BARS + AUX_R + 1024;
   static_assert(SMEM <= 232448, "exceeds the 227 KB shared memory of an sm_100 CTA");
 };
@@ -530,7 +535,7 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
       pm = pm * CG + crank;
       if (IS_FWD) pre0 = s.inv_c[pn * BN + (et & (BN - 1))];
       if (IS_BWDG) {
-        const int i = pn * BN + et;
+        const int i = pn * BN + (et & (BN - 1));
         const bool iv = i < s.B;
         pre0 = iv ? s.negoff[i] : -INFINITY;                  // -(lse_i log2e) + log2(1/B)
         pre1 = iv ? __int_as_float(s.ylocal[i]) : __int_as_float(-1);
@@ -563,6 +568,11 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
 #ifdef ASM_TIMING
     long long e_all = clock64(), e_wait = 0;
 #endif
+    // recompute kernel with sixteen epilogue warps: q_j of the previous tile, written one tile late
+    float q_prev = 0.f;
+    int q_prev_a = 0;
+    long long q_prev_idx = -1;
+    float* qx = reinterpret_cast<float*>(stg + 16 * 2048);   // [2 stages][2 column-group pairs][128 classes]
     for (int u = pair_id; u < total; u += npairs, ++lt) {
       int z, m_idx, n_idx;
       decode(u, z, m_idx, n_idx);
@@ -691,9 +701,11 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
         ASM_EPILOGUE_CHUNKS(process)
       } else if (IS_BWDG) {
         // ---- thread = class j (row m), columns = batch rows i.  Stage the per-row terms.
-        v0[et] = pre0;
-        v1[et] = pre1;
-        v2[et] = pre2;
+        if (et < BN) {
+          v0[et] = pre0;
+          v1[et] = pre1;
+          v2[et] = pre2;
+        }
         const float ic = pre3;                                // fetched one tile ahead
         prefetch_tile(u + npairs);
         const int j = m0 + lane_row;                          // class (< Cp always)
@@ -707,6 +719,12 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
         uint8_t* stg_half = stg + half * NSB * STG_HALF;
         const bool leader = (threadIdx.x == 128 + half * 128);
         named_bar_sync(1, EPI_THREADS);
+        if (EPIW == 16 && q_prev_idx >= 0 && (half & 1) == 0) {
+          // sixteen warps: the q_j partial of the PREVIOUS tile, own 64 columns + the neighbouring
+          // column group's (left in shared memory before the barrier above): two partials per
+          // batch tile as with eight warps, so the dW kernel sums the same number of them
+          s.q_part[q_prev_idx] = q_prev + qx[(q_prev_a * 2 + (half >> 1)) * 128 + lane_row];
+        }
         ptx::mbar_wait(&tfull[a], aph);
         ptx::tc_fence_after();
         float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;         // sum_i G'_ij * acc_ij  (x ic later)
@@ -770,10 +788,12 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
               // own TMA store, so the eight epilogue warps never wait for each other: one
               // __syncwarp per chunk instead of a 128-thread barrier.  Before block (c & 1) is
               // rewritten, lane 0 confirms that the store before last has drained it.
-              uint8_t* sbuf = stg + ((warp - 4) * 2 + ((c * npl + pl) & 1)) * 2048;
+              // (sixteen warps: ONE block per warp -- the store before has had a whole chunk of
+              //  arithmetic to drain it)
+              uint8_t* sbuf = stg + (EPIW == 16 ? (warp - 4) : (warp - 4) * 2 + ((c * npl + pl) & 1)) * 2048;
               uint4* rowp = reinterpret_cast<uint4*>(sbuf + lane * 64);
               const int rsw = (lane >> 1) & 3;
-              if (lane == 0) ptx::bulk_wait_read1();
+              if (lane == 0) { if (EPIW == 16) ptx::bulk_wait_read0(); else ptx::bulk_wait_read1(); }
               __syncwarp();
 #pragma unroll
               for (int b = 0; b < 16; ++b) {
@@ -821,7 +841,15 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
           }
         };
         ASM_EPILOGUE_CHUNKS(process)
-        s.q_part[(size_t)(n_idx * 2 + half) * s.Cp + j] = ((q0 + q1) + (q2 + q3)) * ic;
+        if (EPIW == 16) {
+          const float qv = ((q0 + q1) + (q2 + q3)) * ic;
+          if (half & 1) qx[(a * 2 + (half >> 1)) * 128 + lane_row] = qv;
+          q_prev = qv;
+          q_prev_a = (int)a;
+          q_prev_idx = (long long)(n_idx * 2 + (half >> 1)) * s.Cp + j;
+        } else {
+          s.q_part[(size_t)(n_idx * 2 + half) * s.Cp + j] = ((q0 + q1) + (q2 + q3)) * ic;
+        }
       } else if (KIND == U_DW) {
         // ---- thread = class j, columns = d.  dW[d][j] = acc - Wb[d][j] * q_j / c_j^2
         // The q_j partials and 1/c_j were fetched one tile ahead; the bf16 weight chunks
@@ -1039,6 +1067,11 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
       }
 #undef ASM_EPILOGUE_CHUNKS
     }
+    if (IS_BWDG && EPIW == 16 && lt > 0) {
+      named_bar_sync(1, EPI_THREADS);                        // the last tile's neighbour partials are in place
+      if (q_prev_idx >= 0 && (half & 1) == 0)
+        s.q_part[q_prev_idx] = q_prev + qx[(q_prev_a * 2 + (half >> 1)) * 128 + lane_row];
+    }
 #ifdef ASM_TIMING
     if ((pair_id == 0 || pair_id == npairs / 2) && crank == 0 && lane == 0 && (warp == 4 || warp == 11))
       printf("TIMING kind %d pair %d warp %d: epilogue total %lld cyc, wait tfull %lld\n", KIND, pair_id, warp,
@@ -1136,7 +1169,11 @@ int umma_forward_tiles(int B, int Cp, int num_sms, int cg, int bn) {
   const int nq = (c == 2 && bn == 256 ? Geo<U_FWD, 2, 256>::EPIW : 8) / 4;
   return nq * (umma_forward_grid(B, Cp, num_sms, cg, bn) / c / mt);
 }
-int umma_q_parts(int B, int bn) { return 2 * ((B + bn - 1) / bn); }    // one partial per column half of a batch tile
+// two q_j partials per batch tile (sixteen epilogue warps add theirs up pairwise in shared memory)
+int umma_q_parts(int B, int bn, int cg) {
+  (void)cg;
+  return 2 * ((B + bn - 1) / bn);
+}
 
 int umma_dx_splits(int B, int D, int Cp, int num_sms, int cg) {
   const int c = fwd_cg(B, cg);
