@@ -360,7 +360,7 @@ int run_backward(asm_head* h, const float* stats_all, int n_shards, float* loss_
 
 extern "C" {
 
-const char* asm_version(void) { return "asoftmax_b200 0.2 sm_100a"; }
+const char* asm_version(void) { return "asoftmax_b200 0.3 sm_100a"; }
 
 float asm_lambda(int64_t iteration, float base, float gamma, float power, float lambda_min) {
   const double v = (double)base * pow(1.0 + (double)gamma * (double)iteration, -(double)power);
