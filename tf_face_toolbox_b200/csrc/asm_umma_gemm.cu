@@ -45,8 +45,7 @@ constexpr int BN_FULL = BN;                   // widest tile: sizes the per-tile
 constexpr int A_BYTES = BM * BK * 2;           // 16 KB
 constexpr int B_BYTES = BN * BK * 2;           // 32 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES; // 48 KB
-constexpr int CHUNK_BYTES = 64 * BK * 2;       // one 64-wide MN-major chunk: 8 KB
-constexpr int NUM_THREADS = 384;
+// threads per CTA: 4 role warps + the epilogue warps of the instantiation (Geo::NTHREADS: 384 or 640)
 constexpr int AUX_BARS = 512;                  // barriers + tmem ptr
 constexpr int AUX_VEC = 3 * 2 * BN * 4;        // per-tile vectors: 3 arrays x 2 stages x 256
 constexpr int STG_HALF = 32 * 128 * 2;         // G'' staging per column half: 128 classes x 32 batch rows (bf16)
@@ -122,9 +121,6 @@ __device__ __forceinline__ float fast_ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
-}
-__device__ __forceinline__ void st_bf16(__nv_bfloat16* p, float v) {
-  *p = __float2bfloat16_rn(v);
 }
 // (i == k) ? a : b as one setp + selp (keeps dynamic-index selects out of branch trees)
 __device__ __forceinline__ float sel_eq(int i, int k, float a, float b) {
