@@ -41,7 +41,7 @@ M_MARGIN = 4
 LAMBDA = 5.0      # lambda_min of the SphereFace schedule (timing uses lambda=5)
 LOSS_TOL = {"fp32": 1e-5, "bf16": 2e-3}      # BASELINE.json north_star
 COS_MIN = 0.9999
-ELEM_TOL = {"fp32": 2e-5, "bf16": 2e-2}      # max |dW - oracle| / max |oracle|, every element of the checked shard
+ELEM_TOL = {"fp32": 5e-5, "bf16": 2e-2}      # max |dW - oracle| / max |oracle|, every element of the checked shard
 
 
 def load_peaks():
