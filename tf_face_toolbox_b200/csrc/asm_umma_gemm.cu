@@ -3,16 +3,18 @@
 //
 // One persistent, warp-specialised kernel template (CTA tile 128 x 256 x 64, 4-stage
 // TMA->smem ring, 2 accumulator stages of 256 TMEM columns so the epilogue of tile t
-// overlaps the MMAs of tile t+1), 384 threads:
+// overlaps the MMAs of tile t+1), 384 threads (640 in the paired forward / recompute kernels):
 //   warp 0  : TMA producer (one elected lane)      warp 1 : tcgen05.mma issuer (one lane)
-//   warp 2  : TMEM allocator                       warps 4-11 : epilogue; warp w owns TMEM
-//             lanes 32*(w%4).. and the column half (w-4)/4 of the 256-column accumulator
+//   warp 2  : TMEM allocator; in the paired dW kernel also the issuer of the dW TMA stores
+//   warp 3  : dW: weight-chunk producer; dX: deferred loss sum
+//   warps 4-11 (4-19 with sixteen epilogue warps) : epilogue; warp w owns TMEM lanes
+//             32*(w%4).. and the column group (w-4)/4 of the 256-column accumulator
 //
 //   KIND   D (lanes x columns)          A (M x K)                  B (N x K)
-//   FWD    S   [batch x classes] K=D    Xb [B,D]   K-major         Wb [D,Cp]  MN-major
-//   BWDG   S^T [classes x batch] K=D    Wb [D,Cp]  MN-major        Xb [B,D]   K-major
+//   FWD    S   [batch x classes] K=D    Xb [B,D]   K-major         Wb (below) MN-major
+//   BWDG   S^T [classes x batch] K=D    Wb         MN-major        Xb [B,D]   K-major
 //   DW     dW^T[classes x d]     K=B    G''[Cp,Bp] K-major         Xb [B,D]   MN-major
-//   DX     dX  [batch x d]       K=C    G''[Cp,Bp] MN-major        Wb [D,Cp]  K-major (split-K)
+//   DX     dX  [batch x d]       K=C    G''[Cp,Bp] MN-major        Wb         K-major (split-K)
 // G'' = G' diag(1/c) is kept CLASS-major ([Cp, Bp], batch contiguous): the recompute kernel's
 // threads own a class each, so their 32 batch values of a chunk are 64 contiguous bytes -- four
 // 16-byte shared-memory stores into a 64B-swizzled staging block that one TMA store writes out.
@@ -21,8 +23,10 @@
 // classes in its registers); in BWDG and DW a thread owns a class (the column sums q_j and
 // the 1/c_j scaling are per-thread constants, and for a fixed batch row / fixed d the 32
 // lanes of a warp write 32 consecutive classes of G'' / dW).  The bf16 copy of W keeps the
-// reference's [D, C] orientation (no transpose anywhere), every operand is read by TMA with
-// 128-byte swizzle, and nothing but [B]-sized statistics leaves the forward kernel.
+// reference's orientation (d outer, classes inner: no transpose anywhere) but is stored
+// column-blocked, [Cp/64][D][64], so that every 64-class TMA box is one contiguous piece;
+// every operand is read by TMA with 128-byte swizzle, and nothing but [B]-sized statistics
+// leaves the forward kernel.
 #include <type_traits>
 
 #include "asm_common.cuh"
@@ -510,10 +514,10 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
       if (lane == 0 && s.loss) *s.loss = r * s.invB;
     }
   } else if (warp >= 4) {
-    // ------------------------------------------------------------ epilogue (256 threads)
+    // ------------------------------------------------------------ epilogue (EPIW warps)
     const int q4 = warp & 3;                  // TMEM lane quarter this warp may access
-    const int half = (warp - 4) >> 2;         // which 128 of the 256 accumulator columns
-    const int et = threadIdx.x - 128;         // 0..255
+    const int half = (warp - 4) >> 2;         // column group: which HC of the 256 accumulator columns (0..NQ-1)
+    const int et = threadIdx.x - 128;         // 0 .. 32 EPIW - 1
     const int lane_row = q4 * 32 + lane;      // row of the tile owned by this thread
     const int col0 = half * HC;
     uint32_t lt = 0;
@@ -781,7 +785,7 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
             uint32_t pk[16];
             if (NSB == 2) {
               // CTA pairs: every WARP owns two [32 classes x 32 batch] staging blocks and issues its
-              // own TMA store, so the eight epilogue warps never wait for each other: one
+              // own TMA store, so the epilogue warps never wait for each other: one
               // __syncwarp per chunk instead of a 128-thread barrier.  Before block (c & 1) is
               // rewritten, lane 0 confirms that the store before last has drained it.
               // (sixteen warps: ONE block per warp -- the store before has had a whole chunk of
