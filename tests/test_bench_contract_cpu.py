@@ -47,3 +47,30 @@ def test_product_arm_has_no_cpu_fallback():
     # no measurement may come out of a box without a CUDA device
     assert line is None or line.get("gpu_launches", 0) == 0 and not line.get("value")
     assert "no CUDA device" in (p.stderr + p.stdout)
+
+
+def test_committed_evidence_is_self_consistent():
+    """profiles/: the N = 1 bench line of the final run carries the agreed extra objects, its parity
+    record bounds every element of dW, and the DRAM-traffic file bench.py quotes was captured from
+    the same library version (bench.py refuses it otherwise)."""
+    prof = os.path.join(ROOT, "profiles")
+    line = json.loads(open(os.path.join(prof, "r2_bench_n1.json")).read().strip().splitlines()[-1])
+    for key in ("roofline", "cpu_baseline", "e2e", "clocks", "gpu_launches", "parity", "kernels", "phases", "cfg4",
+                "library", "env"):
+        assert key in line, key
+    assert line["parity"]["ok"] and line["cfg4"]["parity"]["ok"]
+    for rec in line["parity"]["paths"].values():
+        assert rec["max_err_dW"] <= line["parity"]["tolerance"]["max_err_dW_over_max_abs"]
+    roof = line["roofline"]
+    assert roof["bound"] in ("hbm", "tensor") and 0 < roof["frac"] <= 1 and roof["peak"] > 0
+    assert abs(roof["frac"] - roof["achieved"] / roof["peak"]) < 1e-9
+    assert line["e2e"]["h2d_bytes_per_step"] > 0 and line["e2e"]["d2h_bytes_per_step"] > 0
+    assert line["gpu_launches"] == line["steps"] * line["launches_per_step"]
+    traffic = json.load(open(os.path.join(prof, "traffic_cfg3.json")))
+    assert traffic["library_version"] == line["library"]
+    assert abs(sum(traffic["kernels"].values()) - traffic["step_total"]) <= len(traffic["kernels"])
+    # the multi-GPU lines passed their parity gate on every launch path, with identical loss bits
+    for n in (2, 4, 8):
+        ln = json.loads(open(os.path.join(prof, f"r2_bench_n{n}.json")).read().strip().splitlines()[-1])
+        assert ln["n_gpus"] == n and ln["parity"]["ok"]
+        assert all(r["ok"] and r["loss_identical_across_ranks"] for r in ln["parity"]["paths"].values())
