@@ -74,3 +74,35 @@ def test_committed_evidence_is_self_consistent():
         ln = json.loads(open(os.path.join(prof, f"r2_bench_n{n}.json")).read().strip().splitlines()[-1])
         assert ln["n_gpus"] == n and ln["parity"]["ok"]
         assert all(r["ok"] and r["loss_identical_across_ranks"] for r in ln["parity"]["paths"].values())
+
+
+def test_build_line_quotes_the_traffic_capture_of_the_same_library():
+    """bench.py's line builder, fed with the recorded N = 1 measurements: the dominant kernel's
+    roofline carries the per-launch DRAM traffic of the ncu capture -- and drops it for any other
+    library version."""
+    import importlib.util
+    import types
+    spec = importlib.util.spec_from_file_location("bench_module", os.path.join(ROOT, "bench.py"))
+    b = importlib.util.module_from_spec(spec)
+    argv, sys.argv = sys.argv, ["bench.py"]
+    try:
+        spec.loader.exec_module(b)
+    finally:
+        sys.argv = argv
+    line = json.loads(open(os.path.join(ROOT, "profiles", "r2_bench_n1.json")).read().strip().splitlines()[-1])
+    args = types.SimpleNamespace(workload="cfg3", gpus=1, steps=100, warmup=10, mode="bf16", impl="b200")
+    cfg = {"B": 512, "D": 512, "C": 85742}
+
+    def build(version):
+        return b.build_line(args, cfg, 1, "bf16", b.load_peaks(), {k["kernel"]: k["ms"] for k in line["kernels"]},
+                            {p["phase"]: p["ms"] for p in line["phases"]}, line["value"], line["ms_per_step"], "eager",
+                            line["ms_per_step_by_path"], line["ms_per_step_dist"], line["e2e"]["value"],
+                            line["e2e"]["ms_per_step"], line["e2e"]["path"], line["e2e"]["ms_per_step_by_path"], 512, 7,
+                            100, 10, line["clocks"], line["parity"], {}, False, version, True)
+
+    roof = build(line["library"])["roofline"]
+    traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic_cfg3.json")))
+    assert roof["kernel"] == "dw_gemm" and roof["traffic"] == traffic["kernels"]["dw_gemm"]
+    assert roof["traffic"] > roof["algorithmic_bytes"]          # what the kernel really moves vs what it is credited
+    other = build("some other build")["roofline"]
+    assert other["traffic"] is None and "some other build" in other["traffic_source"]
