@@ -72,3 +72,68 @@ def test_head_save_and_restore_with_tower_prefix(tmp_path):
     h3 = Head(torch.zeros(16, 40))
     ck.load_head(str(tmp_path / "tower"), h3)
     assert torch.equal(h3.weights, w)
+
+
+# ---------------------------------------------------------------------------------------
+# Sharded save / restore (world size 2, gloo): every rank holds a class shard of the weights and
+# of the Adam slots; save_head gathers them into the reference's single [D, C] tensors (rank 0
+# writes), load_head hands every rank its slice back (saver.py:30-80, data_parallel.py:186-196).
+# ---------------------------------------------------------------------------------------
+def _ckpt_worker(rank, world, port, prefix, q):
+    import os
+    import torch
+    import torch.distributed as dist
+    from tf_face_toolbox_b200 import _lib
+    from tf_face_toolbox_b200.sharded import ShardedASoftmaxHead, shard_bounds
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        D, C = 8, 37                                             # 37 classes: ragged shards (19 + 18)
+        g = torch.Generator().manual_seed(3)
+        W, M, V = (torch.randn(D, C, generator=g) for _ in range(3))
+        lo, hi = shard_bounds(C, world, rank)
+
+        class Opt:                                               # what save_head / load_head read of an optimizer
+            kind, beta1, beta2 = _lib.OPT_ADAM, 0.5, 0.999
+
+            def __init__(self, s0, s1, step):
+                self.state0, self.state1, self.step = s0, s1, step
+
+        head = ShardedASoftmaxHead(D, C, m=4, mode="fp32", device="cpu", weights_full=W, shard_compute=object())
+        ck.save_head(prefix, head, Opt(M[:, lo:hi].contiguous(), V[:, lo:hi].contiguous(), 6), global_step=41)
+        dist.barrier()
+        t = ck.read_bundle(prefix)                               # the file holds the FULL tensors, reference names
+        assert sorted(t) == sorted([ck.WEIGHTS, ck.WEIGHTS + "/Adam", ck.WEIGHTS + "/Adam_1", "beta1_power",
+                                    "beta2_power", "global_step"])
+        assert t[ck.WEIGHTS].shape == (D, C) and np.array_equal(t[ck.WEIGHTS], W.numpy())
+        assert np.array_equal(t[ck.WEIGHTS + "/Adam"], M.numpy()) and np.array_equal(t[ck.WEIGHTS + "/Adam_1"], V.numpy())
+        fresh = ShardedASoftmaxHead(D, C, m=4, mode="fp32", device="cpu", weights_full=torch.zeros(D, C),
+                                    shard_compute=object())
+        opt = Opt(None, None, 0)
+        step = ck.load_head(prefix, fresh, opt)
+        ok = (step == 41 and torch.equal(fresh.weights, W[:, lo:hi]) and torch.equal(opt.state0, M[:, lo:hi])
+              and torch.equal(opt.state1, V[:, lo:hi]) and opt.step == 6)
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_head_checkpoint_round_trip_world2(tmp_path):
+    import socket
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    prefix = str(tmp_path / "model.ckpt-41")
+    procs = [ctx.Process(target=_ckpt_worker, args=(r, 2, port, prefix, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    outs = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert outs == [(0, True), (1, True)]
